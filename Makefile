@@ -1,0 +1,21 @@
+# Builds libbndm_b200.so (sm_100a) in-tree.  `make` / `python -c "import __graft_entry__ as g; g.build()"`.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v
+SRC       := $(wildcard bndm_b200/csrc/*.cu)
+OBJ       := $(patsubst bndm_b200/csrc/%.cu,build/%.o,$(SRC))
+LIB       := bndm_b200/lib/libbndm_b200.so
+
+all: $(LIB)
+
+build/%.o: bndm_b200/csrc/%.cu bndm_b200/csrc/common.cuh include/bndm_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(LIB): $(OBJ)
+	@mkdir -p bndm_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+
+clean:
+	rm -rf build $(LIB)
+.PHONY: all clean

@@ -1,0 +1,360 @@
+// C ABI of libbndm_b200.so -- see include/bndm_b200.h for the contract of every entry point.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <new>
+
+#include "../../include/bndm_b200.h"
+#include "common.cuh"
+
+namespace bndm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int fail_cuda(cudaError_t e, const char *what) {
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return BNDM_ERR_CUDA;
+}
+
+#define CK(expr)                                        \
+  do {                                                  \
+    cudaError_t e__ = (expr);                           \
+    if (e__ != cudaSuccess) return fail_cuda(e__, #expr); \
+  } while (0)
+
+static bool stream_is_capturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return st != cudaStreamCaptureStatusNone;
+}
+
+}  // namespace bndm
+
+using namespace bndm;
+
+struct bndm_L {
+  const float *L = nullptr;     // caller's matrix (bound, not owned)
+  float *L_hi = nullptr;        // owned: tf32 hi / lo copies for the tcgen05 path
+  float *L_lo = nullptr;
+  int n = 0;
+  int lower_triangular = 0;
+  int sm100 = 0;
+  // workspace (owned), sized for `cap_cols` padded columns
+  int cap_cols = 0;
+  size_t cap_partial = 0;
+  float *z_raw = nullptr, *z_hi = nullptr, *z_lo = nullptr, *partials = nullptr;
+  int64_t ws_bytes = 0;
+  // optional per-launch timing (bndm_profile_enable)
+  int profile = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  int ev_valid = 0;
+};
+
+static const int kUnitCap = 592;   // most partial tiles any schedule may produce per column block
+
+static int pad_cols(int n_cols) {
+  const int nb = tc_pick_nb(n_cols);
+  return (n_cols + nb - 1) / nb * nb;
+}
+
+// Chunk length of the split-K schedule: enough units to fill the 148 SMs for the given
+// number of column blocks, never more than kUnitCap partial tiles.
+static Schedule pick_schedule(int n_row_tiles, int dense, int col_blocks) {
+  Schedule s;
+  s.n_row_tiles = n_row_tiles;
+  s.dense = dense;
+  for (int kc = 8; kc >= 1; --kc) {
+    s.kc = kc;
+    if (s.n_units() * col_blocks >= 148) break;
+  }
+  while (s.n_units() > kUnitCap) ++s.kc;
+  return s;
+}
+
+// fp32 elements of partial-tile workspace a call with n_cols columns may need (any branch)
+static size_t partial_elems(int n_cols) {
+  const int cp = pad_cols(n_cols);
+  const int nb = tc_pick_nb(n_cols);
+  size_t worst = 0;
+  for (int dense = 0; dense < 2; ++dense)
+    for (int rows = kNumBlk / 2; rows <= kNumBlk; rows += kNumBlk / 2)
+      for (int simt = 0; simt < 2; ++simt) {
+        const Schedule s = pick_schedule(rows, dense, simt ? (cp + 63) / 64 : cp / nb);
+        const size_t e = (size_t)s.n_units() * cp * kBlk;
+        if (e > worst) worst = e;
+      }
+  return worst;
+}
+
+static void free_ws(bndm_L *h) {
+  cudaFree(h->z_raw);
+  cudaFree(h->z_hi);
+  cudaFree(h->z_lo);
+  cudaFree(h->partials);
+  h->z_raw = h->z_hi = h->z_lo = h->partials = nullptr;
+  h->cap_cols = 0;
+  h->cap_partial = 0;
+  h->ws_bytes = 0;
+}
+
+static int alloc_ws(bndm_L *h, int max_columns) {
+  free_ws(h);
+  const int cols_pad = pad_cols(max_columns);
+  size_t pe = partial_elems(max_columns);
+  // smaller calls pick finer schedules: cover every single-column-block configuration too
+  const size_t small = (size_t)kUnitCap * (cols_pad < 256 ? cols_pad : 256) * kBlk;
+  if (small > pe) pe = small;
+  const size_t zb = (size_t)cols_pad * kNPix * sizeof(float);
+  CK(cudaMalloc(&h->z_raw, zb));
+  CK(cudaMalloc(&h->z_hi, zb));
+  CK(cudaMalloc(&h->z_lo, zb));
+  CK(cudaMalloc(&h->partials, pe * sizeof(float)));
+  h->cap_cols = cols_pad;
+  h->cap_partial = pe;
+  h->ws_bytes = (int64_t)(3 * zb + pe * sizeof(float));
+  return BNDM_OK;
+}
+
+extern "C" {
+
+int bndm_version(void) { return BNDM_ABI_VERSION; }
+const char *bndm_last_error(void) { return g_err; }
+
+int bndm_device_is_sm100(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+int bndm_prepare_L(const float *L_dev, int n, int max_columns, void *stream, bndm_L **out) {
+  if (!L_dev || !out) { set_error("bndm_prepare_L: null argument"); return BNDM_ERR_ARG; }
+  if (n != kNPix) { set_error("bndm_prepare_L: cov_mat_L must be (4096,4096), got n=%d", n); return BNDM_ERR_UNSUPPORTED; }
+  if (max_columns < 1) max_columns = 1;
+  cudaStream_t s = (cudaStream_t)stream;
+  bndm_L *h = new (std::nothrow) bndm_L();
+  if (!h) { set_error("out of host memory"); return BNDM_ERR_ARG; }
+  h->L = L_dev;
+  h->n = n;
+  h->sm100 = bndm_device_is_sm100();
+
+  int *flag = nullptr;
+  cudaError_t e = cudaMalloc(&flag, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(flag, 0, sizeof(int), s);
+  if (e == cudaSuccess) e = launch_tri_check(L_dev, n, flag, s);
+  int host_flag = 1;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&host_flag, flag, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(flag);
+  if (e != cudaSuccess) { delete h; return fail_cuda(e, "triangularity check"); }
+  h->lower_triangular = host_flag ? 0 : 1;
+
+  if (h->sm100) {
+    const size_t lb = (size_t)n * n * sizeof(float);
+    e = cudaMalloc(&h->L_hi, lb);
+    if (e == cudaSuccess) e = cudaMalloc(&h->L_lo, lb);
+    if (e == cudaSuccess) e = launch_split_tf32(L_dev, h->L_hi, h->L_lo, (int64_t)n * n, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) { bndm_free_L(h); return fail_cuda(e, "tf32 split of L"); }
+  }
+  int rc = alloc_ws(h, max_columns);
+  if (rc != BNDM_OK) { bndm_free_L(h); return rc; }
+  *out = h;
+  return BNDM_OK;
+}
+
+int bndm_reserve_columns(bndm_L *h, int max_columns, void *stream) {
+  if (!h) { set_error("null handle"); return BNDM_ERR_ARG; }
+  if (pad_cols(max_columns) <= h->cap_cols && partial_elems(max_columns) <= h->cap_partial) return BNDM_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (stream_is_capturing(s)) { set_error("workspace growth requested during stream capture"); return BNDM_ERR_WORKSPACE; }
+  CK(cudaStreamSynchronize(s));
+  return alloc_ws(h, max_columns);
+}
+
+int bndm_L_is_lower_triangular(const bndm_L *h) { return h ? h->lower_triangular : 0; }
+int64_t bndm_workspace_bytes(const bndm_L *h) { return h ? h->ws_bytes : 0; }
+
+int bndm_profile_enable(bndm_L *h, int on) {
+  if (!h) { set_error("null handle"); return BNDM_ERR_ARG; }
+  if (on && !h->ev[0])
+    for (int i = 0; i < 4; ++i) CK(cudaEventCreate(&h->ev[i]));
+  h->profile = on ? 1 : 0;
+  h->ev_valid = 0;
+  return BNDM_OK;
+}
+
+int bndm_profile_last_ms(bndm_L *h, float *pack_ms, float *gemm_ms, float *epilogue_ms) {
+  if (!h || !h->ev_valid) { set_error("no profiled call recorded"); return BNDM_ERR_ARG; }
+  CK(cudaEventSynchronize(h->ev[3]));
+  float t[3];
+  for (int i = 0; i < 3; ++i) CK(cudaEventElapsedTime(&t[i], h->ev[i], h->ev[i + 1]));
+  if (pack_ms) *pack_ms = t[0];
+  if (gemm_ms) *gemm_ms = t[1];
+  if (epilogue_ms) *epilogue_ms = t[2];
+  return BNDM_OK;
+}
+
+int bndm_free_L(bndm_L *h) {
+  if (!h) return BNDM_OK;
+  for (int i = 0; i < 4; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  free_ws(h);
+  cudaFree(h->L_hi);
+  cudaFree(h->L_lo);
+  delete h;
+  return BNDM_OK;
+}
+
+int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out, float *out_bn, float *out_wn, int B,
+                       int C, int res, unsigned flags, void *stream) {
+  if (!h || !z || !out) { set_error("bndm_get_noise_f32: null argument"); return BNDM_ERR_ARG; }
+  if (B < 1 || C < 1) { set_error("bndm_get_noise_f32: bad shape B=%d C=%d", B, C); return BNDM_ERR_ARG; }
+  int mode;
+  if (res == 64) mode = kRes64;
+  else if (res == 32) mode = kRes32;
+  else if (res == 128) mode = kRes128;
+  else { set_error("bndm_get_noise_f32: resolution %d not implemented (32/64/128)", res); return BNDM_ERR_UNSUPPORTED; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int src_is_image = (flags & BNDM_SRC_IMAGE) ? 1 : 0;
+  const bool simt = (flags & BNDM_GEMM_SIMT) != 0;
+  if (!simt && !h->sm100) { set_error("tcgen05 path needs an sm_100 device"); return BNDM_ERR_ARCH; }
+  const int dense = (!h->lower_triangular || (flags & BNDM_FORCE_DENSE)) ? 1 : 0;
+
+  const int n_cols = B * C * (mode == kRes128 ? 4 : 1);
+  const int nb = tc_pick_nb(n_cols);
+  const int n_cols_pad = (n_cols + nb - 1) / nb * nb;
+  const Schedule sched = pick_schedule(mode == kRes32 ? kNumBlk / 2 : kNumBlk, dense, simt ? (n_cols_pad + 63) / 64 : n_cols_pad / nb);
+  if (n_cols_pad > h->cap_cols || (size_t)sched.n_units() * n_cols_pad * kBlk > h->cap_partial) {
+    int rc = bndm_reserve_columns(h, n_cols, stream);
+    if (rc != BNDM_OK) return rc;
+  }
+
+  // K1a: the white columns are already in GEMM order unless they are gathered from an image;
+  // the SIMT kernel reads zero-padded columns, so it always goes through the workspace copy.
+  const bool src_packed = !(src_is_image && mode != kRes64);
+  const bool need_raw = simt || !src_packed;
+  PackArgs p;
+  p.src = z;
+  p.z_raw = need_raw ? h->z_raw : nullptr;
+  p.z_hi = simt ? nullptr : h->z_hi;
+  p.z_lo = simt ? nullptr : h->z_lo;
+  p.n_cols = n_cols;
+  p.n_cols_pad = n_cols_pad;
+  p.B = B;
+  p.C = C;
+  p.res_mode = mode;
+  p.src_is_image = src_is_image;
+  const bool prof = h->profile && !stream_is_capturing(s);
+  if (prof) CK(cudaEventRecord(h->ev[0], s));
+  CK(launch_pack(p, s));
+  if (prof) CK(cudaEventRecord(h->ev[1], s));
+  const float *z_cols = need_raw ? h->z_raw : z;
+
+  // K1b: split-K triangular contraction -> partial tiles
+  if (simt) {
+    GemmArgs g;
+    g.L = h->L;
+    g.z = z_cols;
+    g.partials = h->partials;
+    g.n_cols_pad = n_cols_pad;
+    g.sched = sched;
+    CK(launch_gemm_simt(g, s));
+  } else {
+    TcGemmArgs g;
+    g.L_hi = h->L_hi;
+    g.L_lo = h->L_lo;
+    g.z_hi = h->z_hi;
+    g.z_lo = h->z_lo;
+    g.partials = h->partials;
+    g.n_cols_pad = n_cols_pad;
+    g.nb = nb;
+    g.sched = sched;
+    CK(launch_gemm_tc(g, s));
+  }
+
+  if (prof) CK(cudaEventRecord(h->ev[2], s));
+  // K1c: ordered combine + lerp + layout
+  EpilogueArgs ep;
+  ep.partials = h->partials;
+  ep.z_cols = z_cols;
+  ep.gamma = gamma;
+  ep.out = out;
+  ep.out_bn = out_bn;
+  ep.out_wn = out_wn;
+  ep.n_cols = n_cols;
+  ep.n_cols_pad = n_cols_pad;
+  ep.B = B;
+  ep.C = C;
+  ep.res_mode = mode;
+  ep.sched = sched;
+  CK(launch_epilogue(ep, s));
+  if (prof) {
+    CK(cudaEventRecord(h->ev[3], s));
+    h->ev_valid = 1;
+  }
+  return BNDM_OK;
+}
+
+int bndm_white128_reinterpret_f32(const float *x, float *out, int B, int C, void *stream) {
+  if (!x || !out || B < 1 || C < 1) { set_error("bndm_white128_reinterpret_f32: bad argument"); return BNDM_ERR_ARG; }
+  if (x == out) { set_error("bndm_white128_reinterpret_f32: in-place not supported"); return BNDM_ERR_ARG; }
+  CK(launch_white128(x, out, B, C, (cudaStream_t)stream));
+  return BNDM_OK;
+}
+
+static int check_step(const void *x_out, const void *x, const void *d, int B, int C, int HW, int Cd) {
+  if (!x_out || !x || !d) { set_error("iadb step: null argument"); return BNDM_ERR_ARG; }
+  if (B < 1 || C < 1 || HW < 1) { set_error("iadb step: bad shape"); return BNDM_ERR_ARG; }
+  if (Cd != C && Cd != 2 * C) {
+    set_error("iadb step: UNet output has %d channels, expected %d or %d", Cd, C, 2 * C);
+    return BNDM_ERR_UNSUPPORTED;   // the reference's NotImplementedError (iadb_bn.py:331)
+  }
+  return BNDM_OK;
+}
+
+int bndm_iadb_step_f32(float *x_out, const float *x, const float *d, const float *dalpha, const float *dgamma, int B,
+                       int C, int HW, int d_channels, void *stream) {
+  int rc = check_step(x_out, x, d, B, C, HW, d_channels);
+  if (rc != BNDM_OK) return rc;
+  if (!dalpha || (d_channels == 2 * C && !dgamma)) { set_error("iadb step: missing coefficient vector"); return BNDM_ERR_ARG; }
+  IadbArgs a{x_out, x, d, dalpha, dgamma, nullptr, nullptr, nullptr, B, C, HW, d_channels};
+  CK(launch_iadb_step(a, false, (cudaStream_t)stream));
+  return BNDM_OK;
+}
+
+int bndm_iadb_step_sched_f32(float *x_out, const float *x, const float *d, const float *table, int *state,
+                             float *t_next_out, int B, int C, int HW, int d_channels, void *stream) {
+  int rc = check_step(x_out, x, d, B, C, HW, d_channels);
+  if (rc != BNDM_OK) return rc;
+  if (!table || !state) { set_error("iadb sched step: null table/state"); return BNDM_ERR_ARG; }
+  IadbArgs a{x_out, x, d, nullptr, nullptr, table, state, t_next_out, B, C, HW, d_channels};
+  CK(launch_iadb_step(a, true, (cudaStream_t)stream));
+  return BNDM_OK;
+}
+
+int bndm_ddim_step_f32(float *x_out, const float *x, const float *eps, const float *noise, const float *coef, int *state,
+                       float *t_next_out, int B, int clip, int64_t n, void *stream) {
+  if (!x_out || !x || !eps || !coef || n < 1) { set_error("ddim step: bad argument"); return BNDM_ERR_ARG; }
+  DdimArgs a{x_out, x, eps, noise, coef, state, t_next_out, B, clip, n};
+  CK(launch_ddim_step(a, (cudaStream_t)stream));
+  return BNDM_OK;
+}
+
+int bndm_to_uint8_nhwc(const float *x, uint8_t *out, int B, int C, int H, int W, void *stream) {
+  if (!x || !out || B < 1 || C < 1 || H < 1 || W < 1) { set_error("to_uint8: bad argument"); return BNDM_ERR_ARG; }
+  CK(launch_to_u8(x, out, B, C, H * W, (cudaStream_t)stream));
+  return BNDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// Internal helpers shared by the kernels of libbndm_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bndm {
+
+constexpr int kTile = 64;            // blue-noise tile edge
+constexpr int kNPix = kTile * kTile; // 4096 = M = K of the contraction
+constexpr int kBlk = 128;            // row-tile / k-block edge of the triangular schedule
+constexpr int kNumBlk = kNPix / kBlk;
+
+// Output mapping of GEMM column j / row p (see DESIGN.md "K1 addressing")
+enum ResMode : int { kRes64 = 0, kRes32 = 1, kRes128 = 2 };
+
+void set_error(const char *fmt, ...);
+
+// ---- the triangular unit schedule, shared by GEMM kernels and the epilogue ---------------
+// Row tile i covers rows [128 i, 128 i + 128); it needs k-blocks [0, kb(i)) with
+// kb(i) = i + 1 (lower-triangular L) or 32 (dense).  The k range is cut in chunks of `kc`
+// k-blocks; every (row tile, chunk) is one work unit that writes one partial tile.
+struct Schedule {
+  int n_row_tiles;   // 32, or 16 for the 32^2 branch (rows with h >= 32 are never stored)
+  int kc;            // k-blocks per unit
+  int dense;         // 0: lower-triangular, 1: dense
+  __host__ __device__ int kblocks(int i) const { return dense ? kNumBlk : i + 1; }
+  __host__ __device__ int nsplit(int i) const { return (kblocks(i) + kc - 1) / kc; }
+  __host__ __device__ int base(int i) const {
+    int b = 0;
+    for (int r = 0; r < i; ++r) b += nsplit(r);
+    return b;
+  }
+  __host__ __device__ int n_units() const { return base(n_row_tiles); }
+  // unit index -> (row tile, first k-block, number of k-blocks)
+  __host__ __device__ void decode(int u, int &i, int &kb0, int &nkb) const {
+    int r = 0;
+    while (u >= nsplit(r)) { u -= nsplit(r); ++r; }
+    i = r;
+    kb0 = u * kc;
+    int rem = kblocks(r) - kb0;
+    nkb = rem < kc ? rem : kc;
+  }
+};
+
+// ---- launchers (defined in the .cu files) -------------------------------------------------
+struct PackArgs {
+  const float *src;   // white source
+  float *z_raw;       // [n_cols_pad][4096] packed raw columns (may be null if src is already packed)
+  float *z_hi;        // [n_cols_pad][4096] tf32 hi part (null for SIMT path)
+  float *z_lo;        // [n_cols_pad][4096] tf32 lo part
+  int n_cols;         // B*C*(tiles per image)
+  int n_cols_pad;     // rows of the packed buffers (zero-filled above n_cols)
+  int B, C;
+  int res_mode;       // ResMode
+  int src_is_image;   // BNDM_SRC_IMAGE
+};
+cudaError_t launch_pack(const PackArgs &a, cudaStream_t s);
+
+struct GemmArgs {
+  const float *L;        // raw L (SIMT path)
+  const float *z;        // packed raw z columns (SIMT path)
+  float *partials;       // [n_units][n_cols_pad][128]
+  int n_cols_pad;
+  Schedule sched;
+};
+cudaError_t launch_gemm_simt(const GemmArgs &a, cudaStream_t s);
+
+struct EpilogueArgs {
+  const float *partials;
+  const float *z_cols;   // packed raw columns [n_cols_pad][4096] (white values)
+  const float *gamma;    // [B] or null
+  float *out, *out_bn, *out_wn;
+  int n_cols, n_cols_pad;
+  int B, C;
+  int res_mode;
+  Schedule sched;
+};
+cudaError_t launch_epilogue(const EpilogueArgs &a, cudaStream_t s);
+
+cudaError_t launch_white128(const float *x, float *out, int B, int C, cudaStream_t s);
+cudaError_t launch_split_tf32(const float *src, float *hi, float *lo, int64_t n, cudaStream_t s);
+cudaError_t launch_tri_check(const float *L, int n, int *flag_dev, cudaStream_t s);
+
+// tcgen05 path: opaque per-handle state lives in noise_gemm_tc.cu
+struct TcPlan;
+struct TcGemmArgs {
+  const float *L_hi, *L_lo;   // [4096][4096] tf32-split copies of L
+  const float *z_hi, *z_lo;   // [n_cols_pad][4096]
+  float *partials;
+  int n_cols_pad;             // multiple of the column block nb
+  int nb;                     // columns per CTA (multiple of 16, <= 256)
+  Schedule sched;
+};
+cudaError_t launch_gemm_tc(const TcGemmArgs &a, cudaStream_t s);
+int tc_pick_nb(int n_cols);   // column block for a given column count
+
+struct IadbArgs {
+  float *x_out;
+  const float *x, *d;
+  const float *dalpha, *dgamma;   // per-sample [B]                       (direct mode)
+  const float *table;             // rows {dalpha, dgamma, t_next, 0}     (scheduled mode)
+  int *state;                     // {step_idx, blocks_done}              (scheduled mode)
+  float *t_next_out;              // [B] or null
+  int B, C, HW, Cd;
+};
+
+cudaError_t launch_iadb_step(const IadbArgs &a, bool sched, cudaStream_t s);
+
+struct DdimArgs {
+  float *x_out;
+  const float *x, *eps, *noise;
+  const float *coef;   // rows of 8
+  int *state;          // may be null
+  float *t_next_out;
+  int B, clip;
+  int64_t n;
+};
+
+cudaError_t launch_ddim_step(const DdimArgs &a, cudaStream_t s);
+cudaError_t launch_to_u8(const float *x, uint8_t *out, int B, int C, int HW, cudaStream_t s);
+
+// ---- tf32 split (round-to-nearest-away hi, residual lo) -----------------------------------
+__device__ __forceinline__ float tf32_rna(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void tf32_split(float v, float &hi, float &lo) {
+  hi = tf32_rna(v);
+  lo = tf32_rna(__fsub_rn(v, hi));
+}
+
+}  // namespace bndm

@@ -1,0 +1,175 @@
+// K2 / K3 / K4: the per-step sampler updates as single vectorised (128-bit) element-wise
+// kernels.  HBM-bound: each reads x and the UNet output once and writes x once.
+//
+//  K2  IADB   x' = (x + da*d[:, :C]) + dg*d[:, C:2C]   iadb_bn.py:326,329,344; utils.py:218-226;
+//                                                       latent_iadb_bn_diffusers.py:110-117
+//  K3  DDIM   x' = c2*clamp((x - c1*e)/c0) + c3*e [+ c4*noise]      diffusers DDIMScheduler.step
+//                                                       (called at ddim_diffusers.py:680)
+//  K4  u8     round(clamp(x/2+0.5,0,1)*255), NCHW -> NHWC            ddim_diffusers.py:687-688
+//
+// All arithmetic is explicit __f*_rn (no FMA contraction) in the reference's association so
+// results are bit-identical to the torch expressions.
+#include "common.cuh"
+
+namespace bndm {
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+__device__ __forceinline__ float upd1(float x, float d, float a) { return __fadd_rn(x, __fmul_rn(a, d)); }
+__device__ __forceinline__ float upd2(float x, float d1, float a, float d2, float g) {
+  return __fadd_rn(__fadd_rn(x, __fmul_rn(a, d1)), __fmul_rn(g, d2));
+}
+
+// Ends a scheduled step: the last block to finish advances the step index and publishes the
+// next UNet timestep.  Safe because every block has read state[0] before it arrives here.
+__device__ __forceinline__ void finish_scheduled(int *state, float *t_next_out, int B, float t_next) {
+  __shared__ int is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int done = atomicAdd(&state[1], 1);
+    is_last = (done == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    if (t_next_out)
+      for (int b = threadIdx.x; b < B; b += blockDim.x) t_next_out[b] = t_next;
+    if (threadIdx.x == 0) {
+      state[1] = 0;
+      __threadfence();
+      state[0] = state[0] + 1;
+    }
+  }
+}
+
+template <bool kSched, bool kVec>
+__global__ void __launch_bounds__(256) iadb_step_kernel(IadbArgs a) {
+  float sa = 0.f, sg = 0.f, t_next = 0.f;
+  if (kSched) {
+    const int step = a.state[0];
+    const float4 row = ldg4(a.table + 4 * (int64_t)step);
+    sa = row.x; sg = row.y; t_next = row.z;
+  }
+  const bool two = a.Cd == 2 * a.C;
+  constexpr int V = kVec ? 4 : 1;
+  const int hwv = a.HW / V;
+  const int64_t total = (int64_t)a.B * a.C * hwv;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int hw = (int)(idx % hwv) * V;
+    const int64_t bc = idx / hwv;
+    const int b = (int)(bc / a.C), c = (int)(bc - (int64_t)b * a.C);
+    const float da = kSched ? sa : __ldg(a.dalpha + b);
+    const float dg = kSched ? sg : (two ? __ldg(a.dgamma + b) : 0.f);
+    const int64_t xo = bc * a.HW + hw;
+    const int64_t d1 = ((int64_t)b * a.Cd + c) * a.HW + hw;
+    const int64_t d2 = d1 + (int64_t)a.C * a.HW;
+    if (kVec) {
+      const float4 xv = *reinterpret_cast<const float4 *>(a.x + xo);
+      const float4 u = ldg4(a.d + d1);
+      float4 o;
+      if (two) {
+        const float4 v = ldg4(a.d + d2);
+        o.x = upd2(xv.x, u.x, da, v.x, dg); o.y = upd2(xv.y, u.y, da, v.y, dg);
+        o.z = upd2(xv.z, u.z, da, v.z, dg); o.w = upd2(xv.w, u.w, da, v.w, dg);
+      } else {
+        o.x = upd1(xv.x, u.x, da); o.y = upd1(xv.y, u.y, da);
+        o.z = upd1(xv.z, u.z, da); o.w = upd1(xv.w, u.w, da);
+      }
+      *reinterpret_cast<float4 *>(a.x_out + xo) = o;
+    } else {
+      const float xv = a.x[xo];
+      a.x_out[xo] = two ? upd2(xv, a.d[d1], da, a.d[d2], dg) : upd1(xv, a.d[d1], da);
+    }
+  }
+  if (kSched) finish_scheduled(a.state, a.t_next_out, a.B, t_next);
+}
+
+static int grid_for(int64_t work_items, int threads) {
+  // multiple of the SM count, capped at 8 resident blocks per SM; grid-stride covers the rest
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = 148 * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+cudaError_t launch_iadb_step(const IadbArgs &a, bool sched, cudaStream_t s) {
+  const bool vec = (a.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.d) |
+                                        reinterpret_cast<uintptr_t>(a.x_out)) % 16 == 0);
+  const int64_t total = (int64_t)a.B * a.C * (a.HW / (vec ? 4 : 1));
+  const int grid = grid_for(total, 256);
+  if (sched) {
+    if (vec) iadb_step_kernel<true, true><<<grid, 256, 0, s>>>(a);
+    else iadb_step_kernel<true, false><<<grid, 256, 0, s>>>(a);
+  } else {
+    if (vec) iadb_step_kernel<false, true><<<grid, 256, 0, s>>>(a);
+    else iadb_step_kernel<false, false><<<grid, 256, 0, s>>>(a);
+  }
+  return cudaGetLastError();
+}
+
+// -------------------------------------------------------------------------------- DDIM
+__device__ __forceinline__ float ddim1(float x, float e, float z, bool has_noise, int clip, const float c[5]) {
+  float x0 = __fdiv_rn(__fsub_rn(x, __fmul_rn(c[1], e)), c[0]);
+  if (clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+  float o = __fadd_rn(__fmul_rn(c[2], x0), __fmul_rn(c[3], e));
+  if (has_noise) o = __fadd_rn(o, __fmul_rn(c[4], z));
+  return o;
+}
+
+template <bool kVec>
+__global__ void __launch_bounds__(256) ddim_step_kernel(DdimArgs a) {
+  const int step = a.state ? a.state[0] : 0;
+  const float *row = a.coef + 8 * (int64_t)step;
+  const float c[5] = {__ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), __ldg(row + 4)};
+  const float t_next = __ldg(row + 5);
+  const bool hn = a.noise != nullptr;
+  constexpr int V = kVec ? 4 : 1;
+  const int64_t total = a.n / V;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    if (kVec) {
+      const float4 xv = *reinterpret_cast<const float4 *>(a.x + idx * 4);
+      const float4 ev = ldg4(a.eps + idx * 4);
+      float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (hn) zv = ldg4(a.noise + idx * 4);
+      float4 o;
+      o.x = ddim1(xv.x, ev.x, zv.x, hn, a.clip, c); o.y = ddim1(xv.y, ev.y, zv.y, hn, a.clip, c);
+      o.z = ddim1(xv.z, ev.z, zv.z, hn, a.clip, c); o.w = ddim1(xv.w, ev.w, zv.w, hn, a.clip, c);
+      *reinterpret_cast<float4 *>(a.x_out + idx * 4) = o;
+    } else {
+      a.x_out[idx] = ddim1(a.x[idx], a.eps[idx], hn ? a.noise[idx] : 0.f, hn, a.clip, c);
+    }
+  }
+  if (a.state) finish_scheduled(a.state, a.t_next_out, a.B, t_next);
+}
+
+cudaError_t launch_ddim_step(const DdimArgs &a, cudaStream_t s) {
+  uintptr_t al = reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.eps) | reinterpret_cast<uintptr_t>(a.x_out);
+  if (a.noise) al |= reinterpret_cast<uintptr_t>(a.noise);
+  const bool vec = (a.n % 4 == 0) && (al % 16 == 0);
+  const int grid = grid_for(a.n / (vec ? 4 : 1), 256);
+  if (vec) ddim_step_kernel<true><<<grid, 256, 0, s>>>(a);
+  else ddim_step_kernel<false><<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------ uint8 NHWC
+__global__ void __launch_bounds__(256) to_u8_kernel(const float *__restrict__ x, uint8_t *__restrict__ out, int B, int C,
+                                                    int HW) {
+  const int64_t total = (int64_t)B * HW;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = idx / HW, hw = idx - b * HW;
+    for (int c = 0; c < C; ++c) {
+      float v = __fadd_rn(__fdiv_rn(x[(b * C + c) * HW + hw], 2.0f), 0.5f);
+      v = fminf(fmaxf(v, 0.0f), 1.0f);
+      out[idx * C + c] = (uint8_t)__float2int_rn(__fmul_rn(v, 255.0f));   // torch.round = half-to-even
+    }
+  }
+}
+
+cudaError_t launch_to_u8(const float *x, uint8_t *out, int B, int C, int HW, cudaStream_t s) {
+  to_u8_kernel<<<grid_for((int64_t)B * HW, 256), 256, 0, s>>>(x, out, B, C, HW);
+  return cudaGetLastError();
+}
+
+}  // namespace bndm

@@ -1,0 +1,167 @@
+"""Correlated (blue) noise generator -- drop-in for the reference's ``get_noise_v2``
+(bluenoise/get_noise_recent.py:23-196) backed by the sm_100a kernels in csrc/.
+
+Same call surface and return triple ``(noise, noise_bn, noise_wn)``; the white draw stays
+in torch (``torch.randn_like`` / ``torch.randn`` exactly where the reference draws, so
+identical seeds give identical white fields); everything after the draw -- contraction
+with L, transposes, 32^2 tiling/crop, 128^2 tiling and white re-interpretation, the
+white<->blue lerp -- runs in three launches of libbndm_b200.so (pack, tcgen05 GEMM,
+epilogue).  CUDA tensors only.
+"""
+from __future__ import annotations
+
+import weakref
+
+import torch
+
+from . import _lib
+
+BLUE_TYPES = ("gaussianBN", "gaussianRN", "GBN")
+_GEMM_FLAGS = {"tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT}
+
+
+class CovMatL:
+    """Device-side handle of the Cholesky factor ``cov_mat_L`` (iadb_bn.py:83-86): keeps the
+    caller's tensor alive plus the kernel-side operand copies and workspace."""
+
+    def __init__(self, cov_mat_L: torch.Tensor, max_columns: int = 192):
+        L = _lib.require_cuda_f32(cov_mat_L, "cov_mat_L")
+        if L.dim() != 2 or L.shape[0] != L.shape[1]:
+            raise ValueError(f"cov_mat_L must be square, got {tuple(L.shape)}")
+        self.tensor = L
+        self.device = L.device
+        lib = _lib.load()
+        handle = _lib.C.c_void_p()
+        with torch.cuda.device(self.device):
+            rc = lib.bndm_prepare_L(_lib.ptr(L), int(L.shape[0]), int(max_columns),
+                                    _lib.current_stream(self.device), _lib.C.byref(handle))
+        _lib.check(rc, "bndm_prepare_L")
+        self._h = handle
+        self._finalizer = weakref.finalize(self, lib.bndm_free_L, handle)
+
+    @property
+    def lower_triangular(self) -> bool:
+        return bool(_lib.load().bndm_L_is_lower_triangular(self._h))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(_lib.load().bndm_workspace_bytes(self._h))
+
+    def reserve(self, max_columns: int):
+        """Pre-size the workspace (needed before CUDA-graph capture of get_noise_v2)."""
+        with torch.cuda.device(self.device):
+            rc = _lib.load().bndm_reserve_columns(self._h, int(max_columns), _lib.current_stream(self.device))
+        _lib.check(rc, "bndm_reserve_columns")
+
+    def profile(self, on=True):
+        _lib.check(_lib.load().bndm_profile_enable(self._h, 1 if on else 0), "bndm_profile_enable")
+
+    def last_ms(self):
+        """(pack, contraction, epilogue) milliseconds of the last profiled get_noise call."""
+        a, b, c = _lib.C.c_float(), _lib.C.c_float(), _lib.C.c_float()
+        _lib.check(_lib.load().bndm_profile_last_ms(self._h, _lib.C.byref(a), _lib.C.byref(b), _lib.C.byref(c)),
+                   "bndm_profile_last_ms")
+        return a.value, b.value, c.value
+
+    def close(self):
+        self._finalizer()
+
+
+_handles: "dict[tuple, CovMatL]" = {}
+
+
+def prepare_L(cov_mat_L, max_columns: int = 192) -> CovMatL:
+    """Returns the cached handle for this tensor (keyed on storage pointer + device)."""
+    if isinstance(cov_mat_L, CovMatL):
+        return cov_mat_L
+    if not isinstance(cov_mat_L, torch.Tensor):
+        raise TypeError("cov_mat_L must be a torch.Tensor or CovMatL")
+    key = (cov_mat_L.data_ptr(), str(cov_mat_L.device), tuple(cov_mat_L.shape), cov_mat_L._version)
+    h = _handles.get(key)
+    if h is None:
+        for k in [k for k in _handles if k[:2] == key[:2]]:      # same buffer, stale contents
+            _handles.pop(k).close()
+        h = _handles[key] = CovMatL(cov_mat_L, max_columns)
+    return h
+
+
+def _white128_reinterpret(x):
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().bndm_white128_reinterpret_f32(_lib.ptr(x), _lib.ptr(out), x.shape[0], x.shape[1],
+                                                       _lib.current_stream(x.device))
+    _lib.check(rc, "bndm_white128_reinterpret_f32")
+    return out
+
+
+def get_noise_v2(device, x, cov_mat_L, alpha_t, time_step=None, noise_type="gaussian", train_or_test="train",
+                 inplace=False, *, gemm="tc", want=("noise", "bn", "wn")):
+    """Drop-in for bluenoise/get_noise_recent.py:23.
+
+    ``alpha_t`` is the per-sample WHITE fraction gamma (B,) -- out = bn*(1-gamma) + wn*gamma
+    (:91,:116,:160).  ``time_step`` is unused, as in the reference.  Extra keyword-only
+    arguments: ``gemm`` in {'tc' (tcgen05 3xTF32), 'simt' (fp32 FFMA)}; ``want`` lets callers
+    that ignore noise_bn / noise_wn skip writing them (those entries are returned as None).
+    """
+    if x.dim() != 4:
+        raise ValueError("x must be (B, C, H, W)")
+    res = x.shape[-1]
+    bs, dimension = x.shape[0], x.shape[1]
+
+    if noise_type == "gaussian":                                   # :31-67, pass-through
+        if res not in (64, 128):
+            raise NotImplementedError
+        noise = x if inplace else torch.randn_like(x)
+        if res == 128 and train_or_test == "test":                 # :50-56 (built from x, not the draw)
+            noise = _white128_reinterpret(_lib.require_cuda_f32(x, "x"))
+        return noise, noise, noise
+
+    if noise_type == "uniform":
+        # the reference computes a uniform field then fails with an unbound `noise_bn` at :196
+        raise NotImplementedError("noise_type='uniform' never returns in the reference")
+    if noise_type not in BLUE_TYPES:
+        raise NotImplementedError
+    if res not in (32, 64, 128):
+        raise NotImplementedError
+
+    x = _lib.require_cuda_f32(x, "x")
+    if x.shape[-2] != res:
+        raise ValueError("x must be square")
+    L = prepare_L(cov_mat_L, max_columns=bs * dimension * (4 if res == 128 else 1))
+    if L.device != x.device:
+        raise ValueError(f"cov_mat_L is on {L.device}, x on {x.device}")
+
+    # ---- the white field: drawn where and how the reference draws it
+    if inplace:
+        z, src = x, _lib.SRC_IMAGE
+    else:
+        src = _lib.SRC_DRAW
+        if res == 64:
+            z = torch.randn_like(x)                                                    # :108
+        elif res == 32:
+            z = torch.randn(bs, dimension, 64, 64, dtype=x.dtype, device=x.device)     # :78-83 randn_like(tiled x)
+        else:
+            z = torch.randn(bs * 4, dimension, 64, 64).float().to(device)              # :138 (CPU generator)
+            z = _lib.require_cuda_f32(z, "white draw")
+
+    gamma = None
+    if noise_type in ("gaussianBN", "gaussianRN"):
+        gamma = _lib.require_cuda_f32(alpha_t.reshape(-1), "alpha_t")
+        if gamma.numel() != bs:
+            raise ValueError(f"alpha_t must have {bs} entries, got {gamma.numel()}")
+
+    shape = (bs, dimension, res, res)
+    out = torch.empty(shape, dtype=torch.float32, device=x.device)
+    out_bn = torch.empty_like(out) if (gamma is not None and "bn" in want) else None
+    out_wn = torch.empty_like(out) if "wn" in want else None
+    with torch.cuda.device(x.device):
+        rc = _lib.load().bndm_get_noise_f32(L._h, _lib.ptr(z), _lib.ptr(gamma), _lib.ptr(out), _lib.ptr(out_bn),
+                                            _lib.ptr(out_wn), bs, dimension, res, src | _GEMM_FLAGS[gemm],
+                                            _lib.current_stream(x.device))
+    _lib.check(rc, "bndm_get_noise_f32")
+    if gamma is None:          # 'GBN': noise IS noise_bn (:118)
+        out_bn = out
+    return out, out_bn, out_wn
+
+
+get_noise = get_noise_v2   # the name BASELINE.json's north_star uses

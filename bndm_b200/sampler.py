@@ -1,0 +1,244 @@
+"""IADB samplers -- drop-ins for the reference's sampling loops, with the per-step update
+done by one fused kernel of libbndm_b200.so and (optionally) the whole
+[UNet forward -> update] step replayed from one CUDA graph.
+
+Reference surfaces kept:
+  sample_iadb(model, x0, nb_step, scheduler_params)                        iadb_bn.py:287 (reads module ``opt``)
+  sample_iadb(model, x0, nb_step, scheduler_gamma, scheduler_params,
+              out_channel, noise_type, train_or_test, scheduler_alpha)     utils.py:180
+  sample_iadb_conditional(model, x0, x_c, nb_step, scheduler_params)       iadb_bn.py:385
+  IADBScheduler().set_timesteps(n) / .step(model_output, t, x_alpha)       latent_iadb_bn_diffusers.py:75-125
+  sample_latent_iadb(...)                                                  latent_iadb_bn_diffusers.py:524-534
+
+What changed underneath: the reference builds the step coefficients with ~20 tiny kernels
+and one host->device copy per step (iadb_bn.py:306-316) and applies them with 3-5
+element-wise launches (:326-344).  Here the coefficients are a device table computed once
+(schedules.iadb_table), and K2 (csrc/steps.cu) applies a row, writes the next UNet
+timestep and advances the device-side step counter -- so a step has no host work and one
+captured graph serves all T steps.
+"""
+from __future__ import annotations
+
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import _lib
+from .schedules import iadb_table, latent_table
+
+TWO_HEAD = ("gaussianBN", "gaussianRN")
+
+# Module-global options namespace, like iadb_bn.py:69 (`opt = parser.parse_args()`).
+opt = SimpleNamespace(noise_type="gaussianBN", out_channel=6, scheduler_alpha="linear", scheduler_gamma="sigmoid",
+                      scheduler_param=1000.0, train_or_test="test", nb_steps=250)
+
+
+def _expected_out_channels(noise_type, out_channel, C):
+    """Mirrors the branch structure (and NotImplementedError sites) of iadb_bn.py:323-346."""
+    if noise_type in TWO_HEAD:
+        if out_channel in (C, 2 * C):
+            return out_channel
+        raise NotImplementedError
+    if noise_type in ("gaussian", "GBN"):
+        return C
+    raise NotImplementedError
+
+
+class IadbStepper:
+    """Device-resident schedule + K2 launcher for one sampling run of fixed shape."""
+
+    def __init__(self, table_cpu: torch.Tensor, first_t: float, batch: int, device):
+        self.device = torch.device(device)
+        self.n_steps = table_cpu.shape[0]
+        self.table = table_cpu.to(self.device).contiguous()
+        self.state = torch.zeros(2, dtype=torch.int32, device=self.device)       # {step index, blocks done}
+        self.t_vec = torch.full((batch,), first_t, dtype=torch.float32, device=self.device)
+        self._first_t = first_t
+
+    def reset(self):
+        self.state.zero_()
+        self.t_vec.fill_(self._first_t)
+
+    def step_(self, x: torch.Tensor, d: torch.Tensor):
+        """x <- x + dalpha*d[:, :C] (+ dgamma*d[:, C:]) in place; advances t_vec / state."""
+        B, C = x.shape[0], x.shape[1]
+        d = _lib.require_cuda_f32(d, "model output")
+        with torch.cuda.device(self.device):
+            rc = _lib.load().bndm_iadb_step_sched_f32(
+                _lib.ptr(x), _lib.ptr(x), _lib.ptr(d), _lib.ptr(self.table), _lib.ptr(self.state),
+                _lib.ptr(self.t_vec), B, C, x.shape[2] * x.shape[3], d.shape[1], _lib.current_stream(self.device))
+        _lib.check(rc, "bndm_iadb_step_sched_f32")
+        return x
+
+
+def iadb_step(x, d, dalpha, dgamma=None, out=None):
+    """One update with per-sample coefficient vectors (the tensors the reference forms at
+    iadb_bn.py:311-316): returns (x + dalpha*d[:, :C]) + dgamma*d[:, C:]."""
+    x = _lib.require_cuda_f32(x, "x")
+    d = _lib.require_cuda_f32(d, "d")
+    dalpha = _lib.require_cuda_f32(dalpha.reshape(-1), "dalpha")
+    if dgamma is not None:
+        dgamma = _lib.require_cuda_f32(dgamma.reshape(-1), "dgamma")
+    out = torch.empty_like(x) if out is None else out
+    B, C = x.shape[0], x.shape[1]
+    with torch.cuda.device(x.device):
+        rc = _lib.load().bndm_iadb_step_f32(_lib.ptr(out), _lib.ptr(x), _lib.ptr(d), _lib.ptr(dalpha), _lib.ptr(dgamma),
+                                            B, C, x.shape[2] * x.shape[3], d.shape[1], _lib.current_stream(x.device))
+    _lib.check(rc, "bndm_iadb_step_f32")
+    return out
+
+
+class GraphedStep:
+    """[d = model(x, t_vec); K2(x, d)] captured once for a fixed shape and replayed per step.
+    x, t_vec and the step counter are static device buffers the graph reads and writes."""
+
+    def __init__(self, model_call, stepper: IadbStepper, x_static: torch.Tensor, warmup: int = 2):
+        self.stepper = stepper
+        self.x = x_static
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=x_static.device)
+        side.wait_stream(torch.cuda.current_stream(x_static.device))
+        keep = x_static.clone()
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                       # lazy inits (cuDNN plans, workspaces) outside capture
+                stepper.step_(x_static, model_call(x_static, stepper.t_vec))
+        torch.cuda.current_stream(x_static.device).wait_stream(side)
+        x_static.copy_(keep)
+        stepper.reset()
+        with torch.cuda.graph(self.graph, stream=side):
+            stepper.step_(x_static, model_call(x_static, stepper.t_vec))
+        stepper.reset()
+
+    def replay(self):
+        self.graph.replay()
+
+
+def _call_model_iadb(model):
+    return lambda x, t: model(x, t, return_dict=False)[0]
+
+
+@torch.no_grad()
+def _run_iadb(model, x0, x_c, nb_step, scheduler_alpha, scheduler_gamma, scheduler_params, out_channel, noise_type,
+              train_or_test, log_freq, use_graph, alpha_param=1000.0):
+    x0 = _lib.require_cuda_f32(x0, "x0")
+    B, C = x0.shape[0], x0.shape[1]
+    _expected_out_channels(noise_type, out_channel, C)
+    table, first_t = iadb_table(nb_step, scheduler_alpha, scheduler_gamma, tuple(float(p) for p in scheduler_params),
+                                alpha_param)
+    if not (noise_type in TWO_HEAD and out_channel == 2 * C):
+        table[:, 1] = 0.0
+    stepper = IadbStepper(table, first_t, B, x0.device)
+    x = x0.clone()                      # the reference never writes into x0 (iadb_bn.py:326 makes new tensors)
+    call = _call_model_iadb(model)
+    if x_c is not None:
+        x_c = _lib.require_cuda_f32(x_c, "x_c")
+        inner = call
+        call = lambda xx, tt: inner(torch.cat([xx, x_c], 1), tt)          # iadb_bn.py:406
+    if nb_step == 1000:
+        log_freq = 100
+    graphed = GraphedStep(call, stepper, x) if use_graph else None
+
+    x_all, per_step = [], []
+    for t in reversed(range(nb_step)):
+        tic = time.time()
+        if graphed is not None:
+            graphed.replay()
+        else:
+            stepper.step_(x, call(x, stepper.t_vec))
+        per_step.append(time.time() - tic)
+        if train_or_test == "test" and (t % log_freq == 0 or t == nb_step - 1):
+            x_all.append(x.clone())
+    return x, x_all, per_step
+
+
+def sample_iadb(model, x0, nb_step, *args, use_graph=False, **kwargs):
+    """Both reference signatures (see module docstring).  Test mode returns
+    ``(x, x_all, mean_step_seconds)`` like iadb_bn.py:376-378, otherwise ``x``."""
+    if len(args) + len(kwargs) == 1:                  # iadb_bn.py:287 -- (scheduler_params,) + module `opt`
+        scheduler_params = args[0] if args else kwargs["scheduler_params"]
+        o = opt
+        cfg = dict(scheduler_alpha=o.scheduler_alpha, scheduler_gamma=o.scheduler_gamma,
+                   out_channel=o.out_channel, noise_type=o.noise_type, train_or_test=o.train_or_test,
+                   log_freq=25, alpha_param=getattr(o, "scheduler_param", 1000.0))
+    else:                                             # utils.py:180
+        names = ("scheduler_gamma", "scheduler_params", "out_channel", "noise_type", "train_or_test", "scheduler_alpha")
+        bound = dict(zip(names, args))
+        bound.update(kwargs)
+        bound.setdefault("scheduler_alpha", "linear")
+        scheduler_params = bound.pop("scheduler_params")
+        cfg = dict(bound, log_freq=1)
+    x, x_all, per_step = _run_iadb(model, x0, None, nb_step, scheduler_params=scheduler_params, use_graph=use_graph,
+                                   **cfg)
+    if cfg["train_or_test"] == "test":
+        return x, x_all, (float(np.mean(per_step[1:])) if len(per_step) > 1 else float("nan"))
+    return x
+
+
+def sample_iadb_conditional(model, x0, x_c, nb_step, scheduler_params, *, use_graph=False):
+    """iadb_bn.py:385 -- UNet input is cat([x, x_c], 1); returns (x, x_all) in test mode."""
+    o = opt
+    x, x_all, _ = _run_iadb(model, x0, x_c, nb_step, o.scheduler_alpha, o.scheduler_gamma, scheduler_params,
+                            o.out_channel, o.noise_type, o.train_or_test, 25, use_graph,
+                            getattr(o, "scheduler_param", 1000.0))
+    if o.train_or_test == "test":
+        return x, x_all
+    return x
+
+
+# ------------------------------------------------------------------ latent IADB (config 5)
+class IADBScheduler:
+    """latent_iadb_bn_diffusers.py:75-138.  ``noise_type`` / ``out_channels`` are the
+    ``args`` globals that file reads (:108-119)."""
+
+    def __init__(self, num_train_timesteps: int = 1000, noise_type="gaussianBN", out_channels=8):
+        self.num_train_timesteps = num_train_timesteps
+        self.num_inference_steps = None
+        self.noise_type = noise_type
+        self.out_channels = out_channels
+
+    def set_timesteps(self, num_inference_steps: int):
+        self.num_inference_steps = num_inference_steps
+
+    def step(self, model_output, timestep: int, x_alpha):
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating "
+                             "the scheduler")
+        C = x_alpha.shape[1]
+        if self.noise_type in TWO_HEAD:
+            if self.out_channels not in (C, 2 * C):
+                raise NotImplementedError
+        elif self.noise_type != "gaussian":
+            raise NotImplementedError
+        N = self.num_inference_steps
+        d = (timestep + 1) / N - timestep / N                      # python float, as :99-103
+        coef = torch.full((x_alpha.shape[0],), d, dtype=torch.float32, device=x_alpha.device)
+        two = self.noise_type in TWO_HEAD and self.out_channels == 2 * C
+        if not two and model_output.shape[1] != C:
+            raise ValueError("model_output channel count does not match the configured out_channels")
+        return iadb_step(x_alpha, model_output, coef, coef if two else None)
+
+    def add_noise(self, original_samples, noise, alpha):
+        """Forward blend (:127-138) -- training-side helper, plain torch."""
+        return (1 - alpha).view(-1, 1, 1, 1) * original_samples + alpha.view(-1, 1, 1, 1) * noise
+
+
+@torch.no_grad()
+def sample_latent_iadb(model, noise, num_steps, noise_type="gaussianBN", out_channels=8, use_graph=False):
+    """The latent sampling loop latent_iadb_bn_diffusers.py:524-534 (VAE decode left to the
+    caller).  UNet timestep is alpha=(t+1)/N broadcast over the batch (:525-528)."""
+    x = _lib.require_cuda_f32(noise, "noise").clone()
+    B, C = x.shape[0], x.shape[1]
+    table, first_t = latent_table(num_steps)
+    if not (noise_type in TWO_HEAD and out_channels == 2 * C):
+        table[:, 1] = 0.0
+    stepper = IadbStepper(table, first_t, B, x.device)
+    call = _call_model_iadb(model)
+    graphed = GraphedStep(call, stepper, x) if use_graph else None
+    for _ in range(num_steps):
+        if graphed is not None:
+            graphed.replay()
+        else:
+            stepper.step_(x, call(x, stepper.t_vec))
+    return x

@@ -1,0 +1,80 @@
+"""alpha / gamma schedules and the per-step coefficient tables the step kernels read.
+
+``get_scheduler`` / ``get_scheduler_gamma`` keep the reference's call surface
+(iadb_bn.py:90-201 with the module-global ``opt``; utils.py:94-174 with explicit
+``nb_steps``).  They are evaluated ONCE per sampling run on the host in torch fp32 -- the
+same expressions in the same order as the reference's CPU path, because the differences
+gamma(t+1)-gamma(t) are dominated by fp32 cancellation (for tau=1000 the step is the
+constant 0.0039736, not 1/250) -- and uploaded as a (T,4) table.  The reference instead
+re-evaluates ~20 tiny kernels plus one host->device copy per step (iadb_bn.py:306-316).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+_CLIP_MIN = 1e-9
+
+
+def _curve_fraction(shape_fn, x, nb_steps, start_value, end_value):
+    """1 - clamp((f(e) - f(s + t(e-s))) / (f(e) - f(s)), 1e-9, 1), t = x/nb_steps; all fp32
+    tensors shaped like x, evaluated in the reference's order (iadb_bn.py:167-178)."""
+    lo = torch.ones_like(x) * start_value
+    hi = torch.ones_like(x) * end_value
+    f_lo, f_hi = shape_fn(lo), shape_fn(hi)
+    here = shape_fn((x / nb_steps) * (hi - lo) + lo)
+    return 1 - torch.clamp((f_hi - here) / (f_hi - f_lo), _CLIP_MIN, 1)
+
+
+def get_scheduler(x, scheduler, nb_steps, scheduler_param=1000.0):
+    """alpha(t).  'linear' (utils.py:110, iadb_bn.py:106); 'sigmoid' / 'cosine' exist only in
+    iadb_bn.py (:109-138) where ``scheduler_param`` is ``opt.scheduler_param``."""
+    scheduler = scheduler.lower()
+    if scheduler == "linear":
+        return x / nb_steps
+    if scheduler == "sigmoid":
+        return _curve_fraction(lambda v: F.sigmoid(v / 0.9), x, nb_steps, scheduler_param, 3)
+    if scheduler == "cosine":
+        return _curve_fraction(lambda v: torch.cos(v * math.pi / 2) ** (2 * scheduler_param), x, nb_steps, 0.2, 1)
+    raise NotImplementedError
+
+
+def get_scheduler_gamma(x, scheduler, scheduler_params, nb_steps):
+    """gamma(t) = white fraction; scheduler_params = (tau, start, end) (utils.py:120-174)."""
+    tau, s, e = scheduler_params[0], scheduler_params[1], scheduler_params[2]
+    scheduler = scheduler.lower()
+    if scheduler == "linear":
+        return x / nb_steps
+    if scheduler == "sigmoid":
+        return _curve_fraction(lambda v: F.sigmoid(v / tau), x, nb_steps, s, e)
+    if scheduler == "cosine":
+        return _curve_fraction(lambda v: torch.pow(torch.cos(v * math.pi / 2), 2 * tau), x, nb_steps, s, e)
+    raise NotImplementedError
+
+
+def iadb_table(nb_step, scheduler_alpha="linear", scheduler_gamma="sigmoid", scheduler_params=(1000.0, 0.0, 3.0),
+               alpha_param=1000.0):
+    """(T,4) fp32 CPU table, row r <-> loop step t = T-1-r (iadb_bn.py:304-316):
+    {alpha(t+1)-alpha(t), gamma(t+1)-gamma(t), alpha(t) [= the NEXT step's UNet timestep], 0}
+    and the first UNet timestep alpha(T)."""
+    t = torch.arange(nb_step - 1, -1, -1, dtype=torch.int64)          # tt for each row
+    a_start = get_scheduler((t + 1).float(), scheduler_alpha, nb_step, alpha_param)
+    a_end = get_scheduler(t.float(), scheduler_alpha, nb_step, alpha_param)
+    g_start = get_scheduler_gamma((t + 1).float(), scheduler_gamma, scheduler_params, nb_step)
+    g_end = get_scheduler_gamma(t.float(), scheduler_gamma, scheduler_params, nb_step)
+    table = torch.stack([a_start - a_end, g_start - g_end, a_end, torch.zeros_like(a_end)], dim=1).contiguous()
+    return table.float(), float(a_start[0])
+
+
+def latent_table(num_inference_steps):
+    """IADBScheduler.step coefficients (latent_iadb_bn_diffusers.py:99-103): python floats
+    (t+1)/N - t/N for alpha and gamma alike, cast to fp32 when torch multiplies the tensor;
+    UNet timestep alpha = (t+1)/N (:525)."""
+    N = num_inference_steps
+    rows = []
+    for t in reversed(range(N)):
+        d = (t + 1) / N - t / N
+        rows.append([d, d, t / N, 0.0])
+    return torch.tensor(rows, dtype=torch.float64).float().contiguous(), float(torch.tensor(1.0 * N / N))

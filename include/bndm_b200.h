@@ -1,0 +1,134 @@
+/* bndm_b200.h -- C ABI of libbndm_b200.so (sm_100a).
+ *
+ * The reference (xchhuang/bndm) is pure Python: it has no FFI/plugin layer of its own, its
+ * boundary for this path is "Python function call, torch tensors in/out" (SURVEY.md 8b).
+ * This header is the C-ABI a Python (ctypes) / C++ host binds instead of the torch op
+ * sequences cited per entry point.  Plain pointers and sizes only: no torch / C++ types.
+ *
+ * Conventions
+ *   - every pointer marked "dev" is a device pointer on the CURRENT CUDA device, fp32,
+ *     contiguous NCHW, 16-byte aligned (torch allocations are 512-byte aligned);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - all calls are stream-ordered, never synchronise, never allocate inside a
+ *     noise/step call once the handle has enough workspace (=> CUDA-Graph capturable);
+ *   - return value: 0 = ok, negative = error (see enum); bndm_last_error() gives the text
+ *     (thread-local); nothing throws or exits across the ABI;
+ *   - the caller owns every buffer; the library retains no caller pointer past a call,
+ *     except the L pointer bound into the opaque bndm_L handle (must outlive it).
+ */
+#ifndef BNDM_B200_H_
+#define BNDM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNDM_ABI_VERSION 1
+
+enum {
+  BNDM_OK = 0,
+  BNDM_ERR_ARG = -1,          /* null pointer / bad size / misaligned                          */
+  BNDM_ERR_UNSUPPORTED = -2,  /* resolution other than 32/64/128 etc. (the reference's
+                                 NotImplementedError sites, get_noise_recent.py:58,166,187)   */
+  BNDM_ERR_CUDA = -3,         /* a CUDA runtime/driver call failed                             */
+  BNDM_ERR_WORKSPACE = -4,    /* workspace too small while the stream is capturing             */
+  BNDM_ERR_ARCH = -5          /* device is not sm_100 (tcgen05 path requested)                 */
+};
+
+/* ---- flags for bndm_get_noise_f32 ------------------------------------------------------- */
+/* Where the white field comes from (get_noise_recent.py `inplace`):                          */
+#define BNDM_SRC_DRAW     0u  /* z is the torch.randn draw the reference would make:
+                                 res 64: (B,C,64,64) :108 | res 32: (B,C,64,64) :83 (drawn
+                                 AFTER 2x2 tiling) | res 128: (4B,C,64,64) :138                */
+#define BNDM_SRC_IMAGE    1u  /* z is the caller's image x (`inplace=True`): (B,C,res,res);
+                                 res 32 is tiled 2x2 (:78-79), res 128 is cut in quadrants
+                                 concatenated on dim 0 (:131-132)                              */
+/* Which contraction kernel:                                                                 */
+#define BNDM_GEMM_TC      0u  /* tcgen05 / TMA, error-compensated 3xTF32 (default)            */
+#define BNDM_GEMM_SIMT    16u /* fp32 FFMA reference kernel (same results to ~1e-6)           */
+#define BNDM_FORCE_DENSE  32u /* ignore the triangular structure of L (testing)               */
+
+typedef struct bndm_L bndm_L; /* opaque: L + its tcgen05 operand copies + workspace           */
+
+int bndm_version(void);
+const char *bndm_last_error(void);
+
+/* Device capability probe: 1 if the current device can run the tcgen05 path (cc 10.x).      */
+int bndm_device_is_sm100(void);
+
+/* Binds the Cholesky factor `cov_mat_L` (iadb_bn.py:83-86; (n,n) fp32 row-major,
+ * L[p_out][p_in], n must be 4096) and prepares what the kernels need: triangularity check
+ * (README.md:33 says lower-triangular; verified, dense path otherwise), TF32 hi/lo operand
+ * copies for the tcgen05 path, TMA descriptors, workspace for `max_columns` GEMM columns
+ * (columns = B*C*(res==128 ? 4 : 1)).  Synchronises `stream` once (init-time call).        */
+int bndm_prepare_L(const float *L_dev, int n, int max_columns, void *stream, bndm_L **out);
+/* Grow the workspace (not capturable). */
+int bndm_reserve_columns(bndm_L *h, int max_columns, void *stream);
+int bndm_L_is_lower_triangular(const bndm_L *h);
+int64_t bndm_workspace_bytes(const bndm_L *h);
+int bndm_free_L(bndm_L *h);
+
+/* Measurement hook (bench.py roofline): when enabled, bndm_get_noise_f32 brackets its three
+ * launches (K1a pack, K1b contraction, K1c epilogue) with CUDA events on the launch stream;
+ * bndm_profile_last_ms synchronises on the last event and returns the three durations.
+ * Not for use under stream capture.                                                        */
+int bndm_profile_enable(bndm_L *h, int on);
+int bndm_profile_last_ms(bndm_L *h, float *pack_ms, float *gemm_ms, float *epilogue_ms);
+
+/* get_noise_v2, noise_type in {gaussianBN, gaussianRN, GBN}
+ * (bluenoise/get_noise_recent.py:73-164; replaces clone + view/permute + torch.matmul
+ * (expand+bmm) + permute/contiguous + 4 element-wise kernels + the cat/slice tiling):
+ *     bn[b,c,:] = L @ white[b,c,:]   per 64x64 tile
+ *     out       = bn*(1-gamma[b]) + wn*gamma[b]      (gamma == NULL  =>  'GBN': out = bn)
+ * z      dev  white source, layout per BNDM_SRC_* above
+ * gamma  dev  [B] white fraction per sample (the reference's `alpha_t`), or NULL
+ * out    dev  (B,C,res,res)            required
+ * out_bn dev  (B,C,res,res) or NULL    the reference's `noise_bn`
+ * out_wn dev  (B,C,res,res) or NULL    the reference's `noise_wn` (incl. the 128^2
+ *                                      pixel/channel re-interpretation, :143-144)
+ * out/out_bn/out_wn must not alias z.                                                      */
+int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out, float *out_bn,
+                       float *out_wn, int B, int C, int res, unsigned flags, void *stream);
+
+/* 'gaussian' pass-through at 128^2 with train_or_test=='test' (get_noise_recent.py:50-56):
+ * out = noise_padding(reinterpret(quadrants(x))).  x, out: (B,C,128,128), no aliasing.     */
+int bndm_white128_reinterpret_f32(const float *x, float *out, int B, int C, void *stream);
+
+/* IADB update (iadb_bn.py:326,329,344; utils.py:218,221,226; latent...:110,113,117):
+ *     x_out = (x + dalpha[b]*d[:, :C]) + dgamma[b]*d[:, C:2C]      (d_channels == 2C)
+ *     x_out =  x + dalpha[b]*d                                      (d_channels == C)
+ * fp32, no FMA contraction, reference association => bit-exact vs the torch expression.
+ * x_out may alias x.  dalpha/dgamma: dev [B]; dgamma may be NULL when d_channels == C.     */
+int bndm_iadb_step_f32(float *x_out, const float *x, const float *d, const float *dalpha,
+                       const float *dgamma, int B, int C, int HW, int d_channels, void *stream);
+
+/* Same update driven by a device-resident schedule so that ONE captured CUDA graph of
+ * [UNet, step] replays for every t:  row = table[*step_idx]  = {dalpha, dgamma, t_next, 0};
+ * after the update the kernel fills t_next_out[0..B) with row.t_next (the next UNet
+ * "timestep" = alpha_start of the following step, iadb_bn.py:311,319) and increments
+ * *step_idx.  `state` is 2 ints on the device: {step_idx, blocks_done}.                    */
+int bndm_iadb_step_sched_f32(float *x_out, const float *x, const float *d, const float *table,
+                             int *state, float *t_next_out, int B, int C, int HW, int d_channels,
+                             void *stream);
+
+/* DDIM update, epsilon prediction (diffusers DDIMScheduler.step as called at
+ * ddim_diffusers.py:680; parity unpinned, see oracle/sampler.py):
+ *     x0  = clamp((x - c[1]*eps) / c[0], -1, 1)          (clamp iff clip != 0)
+ *     out = (c[2]*x0 + c[3]*eps) [+ c[4]*noise]          (noise may be NULL => eta = 0)
+ * coef: dev, rows of 8 floats {sqrt(abar_t), sqrt(1-abar_t), sqrt(abar_prev),
+ * sqrt(1-abar_prev-sigma^2), sigma, t_next, 0, 0}; row *state (state == NULL => row 0, no
+ * increment).  t_next_out: dev [B] float or NULL.  n = B*C*H*W.  x_out may alias x.        */
+int bndm_ddim_step_f32(float *x_out, const float *x, const float *eps, const float *noise,
+                       const float *coef, int *state, float *t_next_out, int B, int clip, int64_t n,
+                       void *stream);
+
+/* Image post-processing of the test drivers (iadb_bn.py:796-816, ddim_diffusers.py:687-688):
+ * out_u8[b,h,w,c] = round(clamp(x[b,c,h,w]/2 + 0.5, 0, 1) * 255), NCHW fp32 -> NHWC uint8. */
+int bndm_to_uint8_nhwc(const float *x, uint8_t *out, int B, int C, int H, int W, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNDM_B200_H_ */

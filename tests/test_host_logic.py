@@ -1,0 +1,183 @@
+"""CPU: host-side logic of the product (no kernel launches): the C-ABI library loads and
+exports every symbol the header declares, schedules / tables, error behaviour without a
+GPU, sharding (incl. a world_size-2 gloo run), the UNet restatement."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+HEADER = os.path.join(ROOT, "include", "bndm_b200.h")
+
+
+def _declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(bndm_[a-zA-Z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_loads_and_exports_header_symbols():
+    from bndm_b200 import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        subprocess.check_call(["make", "-C", ROOT, "-j8"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 13
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/bndm_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_lib.SIGNATURES) == set(declared)
+    assert lib.bndm_version() == 1
+    assert lib.bndm_last_error() is not None
+
+
+def test_product_refuses_cpu_tensors():
+    import bndm_b200 as bb
+    x = torch.randn(1, 3, 64, 64)
+    L = torch.eye(4096)
+    with pytest.raises(bb.BndmError):
+        bb.get_noise_v2(torch.device("cpu"), x, L, torch.ones(1), None, "gaussianBN", "train", True)
+    with pytest.raises(bb.BndmError):
+        bb.iadb_step(x, x, torch.ones(1))
+    with pytest.raises(NotImplementedError):          # get_noise_recent.py:58-59
+        bb.get_noise_v2(torch.device("cpu"), torch.randn(1, 3, 16, 16), L, None, None, "gaussian")
+    with pytest.raises(NotImplementedError):          # 'uniform' never returns in the reference
+        bb.get_noise_v2(torch.device("cpu"), x, L, None, None, "uniform")
+    with pytest.raises(NotImplementedError):
+        bb.get_noise_v2(torch.device("cpu"), x, L, None, None, "nope")
+
+
+def test_product_does_not_import_oracle():
+    src_dir = os.path.join(ROOT, "bndm_b200")
+    for fn in os.listdir(src_dir):
+        if fn.endswith(".py"):
+            assert "oracle" not in re.sub(r'""".*?"""', "", open(os.path.join(src_dir, fn)).read(), flags=re.S), fn
+
+
+def test_schedule_functions_match_golden():
+    from bndm_b200 import get_scheduler, get_scheduler_gamma
+    g = load_golden("schedules")
+    for key in g.files:
+        parts = key.split("_")
+        T = int(parts[-1][1:])
+        x = torch.arange(0, T + 1).float()
+        if parts[0] == "alpha":
+            got = get_scheduler(x, "linear", T)
+        else:
+            p = (float(parts[2][3:]), float(parts[3][1:]), float(parts[4][1:]))
+            got = get_scheduler_gamma(x, parts[1], p, T)
+        assert np.array_equal(got.numpy(), g[key]), key
+
+
+def test_iadb_table_rows_are_the_reference_differences():
+    from bndm_b200.schedules import iadb_table, latent_table
+    from oracle.sampler import _coefficients
+    T = 250
+    table, first = iadb_table(T, "linear", "sigmoid", (1000.0, 0.0, 3.0))
+    assert table.shape == (T, 4) and first == 1.0
+    for row, t in enumerate(reversed(range(T))):
+        a_s, a_e, g_s, g_e = _coefficients(t, 1, "cpu", T, "linear", "sigmoid", (1000.0, 0.0, 3.0))
+        assert table[row, 0] == (a_s - a_e)[0] and table[row, 1] == (g_s - g_e)[0] and table[row, 2] == a_e[0]
+    # tau=1000 makes d_gamma the cancellation-dominated constant 0.0039736032
+    assert abs(float(table[0, 1]) - 0.0039736032) < 1e-9
+    assert abs(float(table[:, 0].double().sum()) - 1.0) < 1e-6       # telescoping: sum d_alpha = 1
+    lt, lfirst = latent_table(250)
+    assert lfirst == 1.0 and float(lt[0, 0]) == np.float32(250 / 250 - 249 / 250)
+
+
+def test_ddim_scheduler_tables_match_oracle():
+    from bndm_b200 import DDIMScheduler
+    from oracle.sampler import DDIMTables
+    for n, eta in ((100, 0.0), (50, 1.0), (1000, 0.5)):
+        s = DDIMScheduler()
+        s.set_timesteps(n)
+        o = DDIMTables()
+        o.set_timesteps(n)
+        assert list(map(int, s.timesteps)) == list(map(int, o.timesteps))
+        tb = s.coefficient_table(eta)
+        for i, t in enumerate(o.timesteps):
+            want = [float(v) for v in o.coefficients(int(t), eta)]
+            assert [float(v) for v in tb[i, :5]] == want
+        assert float(tb[-1, 5]) == 0.0 and float(tb[0, 5]) == float(o.timesteps[1])
+    with pytest.raises(ValueError):
+        DDIMScheduler().step(torch.zeros(1), 0, torch.zeros(1))
+
+
+def test_shard_bounds_cover_batch():
+    from bndm_b200.dist import global_white_draw, shard_bounds
+    for B, W in ((256, 8), (128, 8), (64, 1), (10, 4), (3, 8)):
+        spans = [shard_bounds(B, r, W) for r in range(W)]
+        assert spans[0][0] == 0 and spans[-1][1] == B
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(W - 1))
+    full = global_white_draw((8, 3, 4, 4), 0, 0, 1)
+    parts = torch.cat([global_white_draw((8, 3, 4, 4), 0, r, 4) for r in range(4)])
+    assert torch.equal(full, parts)
+    np.random.seed(0)
+    assert np.array_equal(full.numpy(), np.random.randn(8, 3, 4, 4).astype(np.float32))   # iadb_bn.py:75,761
+
+
+_GLOO_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["BNDM_ROOT"])
+from bndm_b200.dist import broadcast_L, gather_images, global_white_draw, shard_bounds, broadcast_module
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % os.environ["PORT"],
+                        rank=int(os.environ["RANK"]), world_size=2)
+r = dist.get_rank()
+L = torch.arange(16.).reshape(4, 4) if r == 0 else torch.zeros(4, 4)
+broadcast_L(L)
+assert torch.equal(L, torch.arange(16.).reshape(4, 4))
+lin = torch.nn.Linear(3, 3); broadcast_module(lin)
+w = [torch.empty_like(lin.weight) for _ in range(2)]; dist.all_gather(w, lin.weight.data); assert torch.equal(w[0], w[1])
+B = 5
+mine = global_white_draw((B, 3, 2, 2), 7, r, 2)
+lo, hi = shard_bounds(B, r, 2)
+assert mine.shape[0] == hi - lo
+out = gather_images(mine * 2, B)                      # "sampling" = independent per-sample work
+full = global_white_draw((B, 3, 2, 2), 7, 0, 1) * 2
+assert torch.equal(out, full), (out, full)
+dist.destroy_process_group()
+print("ok", r)
+"""
+
+
+def test_sharding_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER)
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), PORT=str(port), BNDM_ROOT=ROOT)
+        procs.append(subprocess.Popen([sys.executable, str(script)], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out.decode()
+
+
+def test_unet_restatement_shapes_and_keys():
+    from bndm_b200.unet import count_forward_flops, get_latent_model, get_model
+    m = get_model(3, 6, 64)
+    assert abs(sum(p.numel() for p in m.parameters()) / 1e6 - 113.7) < 0.1
+    assert abs(count_forward_flops(m, 64, 64) / 1e9 - 31.06) < 0.05
+    keys = m.state_dict().keys()
+    for k in ("conv_in.weight", "time_embedding.linear_1.weight", "down_blocks.0.resnets.0.norm1.weight",
+              "down_blocks.0.downsamplers.0.conv.weight", "down_blocks.4.attentions.1.to_q.weight",
+              "down_blocks.4.attentions.0.to_out.0.bias", "mid_block.attentions.0.group_norm.weight",
+              "mid_block.resnets.1.time_emb_proj.weight", "up_blocks.1.attentions.2.to_v.weight",
+              "up_blocks.0.upsamplers.0.conv.weight", "up_blocks.5.resnets.2.conv_shortcut.weight",
+              "conv_norm_out.weight", "conv_out.bias"):
+        assert k in keys, k
+    assert not any(k.startswith("down_blocks.5.downsamplers") or k.startswith("up_blocks.5.upsamplers") for k in keys)
+    small = get_latent_model(256, 8).eval()
+    x = torch.randn(2, 4, 16, 16)
+    with torch.no_grad():
+        a = small(x, torch.tensor(0.5), return_dict=False)[0]
+        b = small(x, torch.tensor([0.5, 0.5])).sample
+        c = small(x, 0.5).sample
+    assert a.shape == (2, 8, 16, 16) and torch.equal(a, b) and torch.equal(a, c)

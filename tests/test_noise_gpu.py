@@ -1,0 +1,229 @@
+"""GPU parity: get_noise_v2 (libbndm_b200.so through the C ABI) against the CPU oracle, the
+reference-generated golden vectors and size-independent properties."""
+import numpy as np
+import pytest
+import torch
+
+import bndm_b200 as bb
+from bndm_b200 import _lib
+from conftest import ATOL, NOISE_GOLDENS, RTOL, load_golden
+from oracle import noise as on
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+GEMMS = ["tc", "simt"]
+
+
+@pytest.fixture(scope="module")
+def L_dev(L_np):
+    return torch.from_numpy(L_np).to(DEV)
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def test_native_library_is_loaded():
+    lib = _lib.load()
+    assert lib.bndm_version() == 1
+    with torch.cuda.device(DEV):
+        assert lib.bndm_device_is_sm100() == 1, "tests expect a B200 (sm_100)"
+    with open("/proc/self/maps") as f:
+        assert "libbndm_b200.so" in f.read()
+
+
+@pytest.mark.parametrize("gemm", GEMMS)
+@pytest.mark.parametrize("name", NOISE_GOLDENS)
+def test_golden(name, gemm, L_dev):
+    g = load_golden(name)
+    nt, inplace, tt = str(g["noise_type"]), bool(g["inplace"]), str(g["train_or_test"])
+    x = torch.from_numpy(g["x"].copy()).to(DEV)
+    gamma = torch.from_numpy(g["gamma"]).to(DEV)
+    if inplace or nt == "gaussian":
+        out, bn, wn = bb.get_noise_v2(DEV, x, L_dev, gamma, None, nt, tt, inplace, gemm=gemm)
+    else:
+        # replay the reference's draw: the C-ABI call takes the white field explicitly
+        out, bn, wn = _call_with_draw(L_dev, torch.from_numpy(g["draw"]).to(DEV), gamma, x.shape, nt, gemm)
+    np.testing.assert_allclose(_np(out), g["out"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(_np(bn), g["bn"], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(_np(wn), g["wn"])
+
+
+def _call_with_draw(L_dev, draw, gamma, shape, noise_type, gemm):
+    bs, C, res, _ = shape
+    h = bb.prepare_L(L_dev)
+    out = torch.empty(shape, device=DEV)
+    bn = torch.empty(shape, device=DEV)
+    wn = torch.empty(shape, device=DEV)
+    g = None if noise_type == "GBN" else gamma
+    rc = _lib.load().bndm_get_noise_f32(h._h, _lib.ptr(draw), _lib.ptr(g), _lib.ptr(out), _lib.ptr(bn), _lib.ptr(wn),
+                                        bs, C, res, _lib.SRC_DRAW | {"tc": 0, "simt": 16}[gemm],
+                                        _lib.current_stream(DEV))
+    _lib.check(rc, "bndm_get_noise_f32")
+    return out, bn, wn
+
+
+CASES = [(64, 4, 3), (64, 1, 1), (64, 7, 4), (64, 64, 3), (32, 3, 4), (32, 1, 1), (128, 2, 3), (128, 1, 4),
+         (128, 5, 3), (64, 100, 3)]
+
+
+@pytest.mark.parametrize("gemm", GEMMS)
+@pytest.mark.parametrize("noise_type", ["gaussianBN", "GBN"])
+@pytest.mark.parametrize("res,bs,C", CASES)
+def test_vs_oracle_inplace(res, bs, C, noise_type, gemm, L_np, L_dev):
+    rng = np.random.default_rng(res + 7 * bs + C)
+    x = rng.standard_normal((bs, C, res, res)).astype(np.float32)
+    gamma = rng.random(bs).astype(np.float32)
+    want = on.get_noise_np(x, L_np, gamma, noise_type, "train", True)
+    xt = torch.from_numpy(x).to(DEV)
+    got = bb.get_noise_v2(DEV, xt, L_dev, torch.from_numpy(gamma).to(DEV), None, noise_type, "train", True, gemm=gemm)
+    assert torch.equal(xt.cpu(), torch.from_numpy(x)), "input must not be modified"
+    for g_, w_, nm in zip(got, want, ("noise", "bn", "wn")):
+        assert tuple(g_.shape) == w_.shape, nm
+        if nm == "wn":
+            assert np.array_equal(_np(g_), w_)
+        else:
+            np.testing.assert_allclose(_np(g_), w_, rtol=RTOL, atol=ATOL, err_msg=nm)
+    if noise_type == "GBN":
+        assert got[0] is got[1]                      # get_noise_recent.py:118: noise = noise_bn
+
+
+@pytest.mark.parametrize("res,bs,C", [(64, 3, 3), (32, 2, 4), (128, 2, 3)])
+def test_draw_path_uses_torch_rng_like_reference(res, bs, C, L_np, L_dev):
+    x = torch.zeros(bs, C, res, res, device=DEV)
+    gamma = torch.rand(bs, device=DEV)
+    torch.manual_seed(11)
+    got = bb.get_noise_v2(DEV, x, L_dev, gamma, None, "gaussianBN", "train", False)
+    torch.manual_seed(11)                           # replay the draw exactly as the reference issues it
+    if res == 64:
+        draw = torch.randn_like(x)
+    elif res == 32:
+        draw = torch.randn_like(torch.zeros(bs, C, 64, 64, device=DEV))
+    else:
+        draw = torch.randn(bs * 4, C, 64, 64).float().to(DEV)
+    want = on.get_noise_np(_np(x), L_np, _np(gamma), "gaussianBN", "train", False, _np(draw))
+    np.testing.assert_allclose(_np(got[0]), want[0], rtol=RTOL, atol=ATOL)
+    assert np.array_equal(_np(got[2]), want[2])
+
+
+def test_gaussian_passthrough(L_dev):
+    x64 = torch.randn(2, 3, 64, 64, device=DEV)
+    a, b, c = bb.get_noise_v2(DEV, x64, L_dev, None, None, "gaussian", "train", True)
+    assert a is x64 and b is x64 and c is x64
+    x = torch.randn(3, 3, 128, 128, device=DEV)
+    got = bb.get_noise_v2(DEV, x, L_dev, None, None, "gaussian", "test", True)[0]
+    want = on.get_noise_np(_np(x), None, None, "gaussian", "test", True)[0]
+    assert np.array_equal(_np(got), want)
+    torch.manual_seed(3)
+    tr = bb.get_noise_v2(DEV, x, L_dev, None, None, "gaussian", "train", False)[0]
+    torch.manual_seed(3)
+    assert torch.equal(tr, torch.randn_like(x))
+
+
+def test_errors_mirror_reference(L_dev):
+    with pytest.raises(NotImplementedError):
+        bb.get_noise_v2(DEV, torch.randn(1, 3, 16, 16, device=DEV), L_dev, torch.ones(1, device=DEV), None, "gaussianBN")
+    with pytest.raises(NotImplementedError):
+        bb.get_noise_v2(DEV, torch.randn(1, 3, 256, 256, device=DEV), L_dev, None, None, "gaussian")
+    with pytest.raises(ValueError):
+        bb.get_noise_v2(DEV, torch.randn(2, 3, 64, 64, device=DEV), L_dev, torch.ones(3, device=DEV), None, "gaussianBN",
+                        "train", True)
+    with pytest.raises(NotImplementedError):       # bndm_prepare_L: L must be (4096, 4096)
+        bb.prepare_L(torch.eye(1024, device=DEV))
+
+
+# ------------------------------------------------------------------ properties (any size)
+@pytest.mark.parametrize("gemm", GEMMS)
+def test_gamma_one_is_white_and_gamma_zero_is_blue(gemm, L_dev):
+    x = torch.randn(6, 3, 64, 64, device=DEV)
+    one = torch.ones(6, device=DEV)
+    out, bn, wn = bb.get_noise_v2(DEV, x, L_dev, one, None, "gaussianBN", "train", True, gemm=gemm)
+    assert torch.equal(wn, x)
+    assert torch.equal(out, bn * 0.0 + x)           # bn*(1-1) + wn*1, exactly
+    out0, bn0, _ = bb.get_noise_v2(DEV, x, L_dev, one * 0, None, "gaussianBN", "train", True, gemm=gemm)
+    assert torch.equal(out0, bn0 + x * 0.0)
+
+
+@pytest.mark.parametrize("gemm", GEMMS)
+def test_identity_L_returns_white(gemm):
+    L = torch.eye(4096, device=DEV)
+    x = torch.randn(5, 3, 64, 64, device=DEV)
+    bn = bb.get_noise_v2(DEV, x, L, None, None, "GBN", "train", True, gemm=gemm)[1]
+    # 3xTF32 reconstructs hi+lo exactly up to the dropped 2^-22 term
+    np.testing.assert_allclose(_np(bn), _np(x), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("gemm", GEMMS)
+def test_linearity_and_determinism(gemm, L_dev):
+    a = torch.randn(4, 3, 64, 64, device=DEV)
+    b = torch.randn(4, 3, 64, 64, device=DEV)
+    f = lambda t: bb.get_noise_v2(DEV, t, L_dev, None, None, "GBN", "train", True, gemm=gemm)[1]
+    np.testing.assert_allclose(_np(f(a + b)), _np(f(a) + f(b)), rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(_np(f(a * 2.0)), _np(f(a) * 2.0), rtol=1e-6, atol=1e-6)
+    assert torch.equal(f(a), f(a)), "split-K combine must be run-to-run reproducible"
+
+
+@pytest.mark.parametrize("gemm", GEMMS)
+def test_triangular_skip_equals_dense(gemm, L_np, L_dev):
+    x = torch.randn(3, 3, 64, 64, device=DEV)
+    h = bb.prepare_L(L_dev)
+    assert h.lower_triangular
+    outs = []
+    for extra in (0, _lib.FORCE_DENSE):
+        o = torch.empty_like(x)
+        rc = _lib.load().bndm_get_noise_f32(h._h, _lib.ptr(x), None, _lib.ptr(o), None, None, 3, 3, 64,
+                                            _lib.SRC_IMAGE | {"tc": 0, "simt": 16}[gemm] | extra,
+                                            _lib.current_stream(DEV))
+        _lib.check(rc, "get_noise")
+        outs.append(o)
+    np.testing.assert_allclose(_np(outs[0]), _np(outs[1]), rtol=RTOL, atol=ATOL)
+    # a genuinely dense L is detected and handled
+    rng = np.random.default_rng(3)
+    Ld = (rng.standard_normal((4096, 4096)) / 64).astype(np.float32)
+    hd = bb.prepare_L(torch.from_numpy(Ld).to(DEV))
+    assert not hd.lower_triangular
+    got = bb.get_noise_v2(DEV, x, hd, None, None, "GBN", "train", True, gemm=gemm)[1]
+    want = on.get_noise_np(_np(x), Ld, None, "GBN", "train", True)[1]
+    np.testing.assert_allclose(_np(got), want, rtol=RTOL, atol=ATOL)
+
+
+def test_tc_matches_simt_closely(L_dev):
+    x = torch.randn(64, 3, 64, 64, device=DEV)
+    g = torch.rand(64, device=DEV)
+    a = bb.get_noise_v2(DEV, x, L_dev, g, None, "gaussianBN", "train", True, gemm="tc")[0]
+    b = bb.get_noise_v2(DEV, x, L_dev, g, None, "gaussianBN", "train", True, gemm="simt")[0]
+    err = (a - b).abs().max().item()
+    assert err < 5e-6, err
+
+
+def test_blue_spectrum_is_high_pass():
+    """The figure script's check (scripts/fig_main_3_4_inset_10_supp_1_2.py:31-36,121-122): the
+    power spectrum of L.z for a blue-noise L has (much) less energy at low frequencies."""
+    from bndm_b200.synth import blue_noise_L
+    L = torch.from_numpy(blue_noise_L()).to(DEV)
+    x = torch.randn(32, 3, 64, 64, device=DEV)
+    bn = bb.get_noise_v2(DEV, x, L, None, None, "GBN", "train", True)[1]
+    spec = torch.fft.fft2(bn).abs().pow(2).mean(dim=(0, 1))
+    fy = torch.fft.fftfreq(64, device=DEV)
+    fr = (fy[:, None] ** 2 + fy[None, :] ** 2).sqrt()
+    low, high = spec[(fr > 0) & (fr < 0.1)].mean(), spec[fr > 0.35].mean()
+    assert low < 0.2 * high, (low.item(), high.item())
+    np.testing.assert_allclose(bn.var().item(), 1.0, rtol=0.05)         # unit-diagonal covariance
+
+
+def test_cuda_graph_capture_of_get_noise(L_dev):
+    x = torch.randn(4, 3, 64, 64, device=DEV)
+    g = torch.rand(4, device=DEV)
+    h = bb.prepare_L(L_dev)
+    h.reserve(12)
+    eager = bb.get_noise_v2(DEV, x, h, g, None, "gaussianBN", "train", True)[0].clone()
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.graph(graph, stream=s):
+        out = bb.get_noise_v2(DEV, x, h, g, None, "gaussianBN", "train", True)[0]
+    x.copy_(torch.randn_like(x))
+    graph.replay()
+    torch.cuda.synchronize()
+    again = bb.get_noise_v2(DEV, x, h, g, None, "gaussianBN", "train", True)[0]
+    assert torch.equal(out, again) and not torch.equal(out, eager)

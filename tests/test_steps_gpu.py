@@ -1,0 +1,172 @@
+"""GPU parity: the step kernels (K2 IADB, K3 DDIM, K4 uint8) and the samplers built on them,
+through the C ABI, against the oracle / golden vectors.  Element-wise fp32 work with the
+reference's association => bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import bndm_b200 as bb
+from bndm_b200 import sampler as bs
+from bndm_b200.ddim import sample_ddim
+from conftest import ATOL, RTOL, SAMPLER_GOLDENS, load_golden
+from oracle import sampler as osam
+from oracle.toy import ToyCond, ToyEps
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("B,C,H,two", [(64, 3, 64, True), (5, 3, 16, True), (3, 4, 64, True), (7, 3, 64, False),
+                                       (2, 3, 5, True), (1, 1, 1, False), (16, 4, 64, False), (32, 3, 128, True)])
+def test_iadb_step_bit_exact(B, C, H, two):
+    x = torch.randn(B, C, H, H, device=DEV)
+    d = torch.randn(B, 2 * C if two else C, H, H, device=DEV)
+    da, dg = torch.rand(B, device=DEV) * 0.01, torch.rand(B, device=DEV) * 0.01
+    want = osam.iadb_update(x, d, da, dg, "gaussianBN", d.shape[1])
+    got = bb.iadb_step(x, d, da, dg if two else None)
+    assert torch.equal(got, want)
+    # in place
+    x2 = x.clone()
+    bb.iadb_step(x2, d, da, dg if two else None, out=x2)
+    assert torch.equal(x2, want)
+    # CPU oracle gives the same bits (IEEE mul/add)
+    want_cpu = osam.iadb_update(x.cpu(), d.cpu(), da.cpu(), dg.cpu(), "gaussianBN", d.shape[1])
+    assert torch.equal(got.cpu(), want_cpu)
+
+
+def test_iadb_step_rejects_bad_channel_count():
+    x = torch.randn(2, 3, 8, 8, device=DEV)
+    with pytest.raises(NotImplementedError):
+        bb.iadb_step(x, torch.randn(2, 5, 8, 8, device=DEV), torch.ones(2, device=DEV), torch.ones(2, device=DEV))
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+@pytest.mark.parametrize("name", SAMPLER_GOLDENS)
+def test_sample_iadb_matches_reference_golden_bitwise(name, use_graph):
+    g = load_golden(name)
+    oc, nt, T = int(g["out_channel"]), str(g["noise_type"]), int(g["nb_step"])
+    x0 = torch.from_numpy(g["x0"].copy()).to(DEV)
+    x, x_all, secs = bb.sample_iadb(ToyEps(oc), x0, T, "sigmoid", tuple(g["scheduler_params"]), oc, nt, "test",
+                                    use_graph=use_graph)
+    assert torch.equal(x0.cpu(), torch.from_numpy(g["x0"])), "x0 must not be modified"
+    assert len(x_all) == int(g["n_snaps"]) and np.isfinite(secs)
+    assert np.array_equal(x.cpu().numpy(), g["x"])
+    for i, idx in enumerate(g["snap_idx"]):
+        assert np.array_equal(x_all[int(idx)].cpu().numpy(), g["snaps"][i])
+
+
+def test_sample_iadb_opt_signature_and_train_mode():
+    x0 = torch.randn(3, 3, 16, 16, device=DEV)
+    bs.opt.noise_type, bs.opt.out_channel, bs.opt.train_or_test = "gaussianBN", 6, "test"
+    bs.opt.scheduler_alpha, bs.opt.scheduler_gamma = "linear", "sigmoid"
+    x, x_all, _ = bb.sample_iadb(ToyEps(6), x0, 250, (1000.0, 0.0, 3.0))
+    want, wall, _ = osam.sample_iadb_opt(ToyEps(6), x0.cpu(), 250, (1000.0, 0.0, 3.0), osam.make_opt())
+    assert torch.equal(x.cpu(), want) and len(x_all) == len(wall) == 11
+    for a, b in zip(x_all, wall):
+        assert torch.equal(a.cpu(), b)
+    bs.opt.train_or_test = "train"
+    y = bb.sample_iadb(ToyEps(6), x0, 50, (0.2, 0.0, 3.0))
+    assert torch.is_tensor(y)
+    assert torch.equal(y.cpu(), osam.sample_iadb_opt(ToyEps(6), x0.cpu(), 50, (0.2, 0.0, 3.0),
+                                                     osam.make_opt(train_or_test="train")))
+    bs.opt.train_or_test = "test"
+    bs.opt.noise_type = "bogus"
+    with pytest.raises(NotImplementedError):
+        bb.sample_iadb(ToyEps(6), x0, 5, (0.2, 0.0, 3.0))
+    bs.opt.noise_type = "gaussianBN"
+
+
+def test_sample_iadb_conditional():
+    x0 = torch.randn(2, 3, 16, 16, device=DEV)
+    xc = torch.randn(2, 3, 16, 16, device=DEV)
+    bs.opt.noise_type, bs.opt.out_channel, bs.opt.train_or_test = "gaussianBN", 6, "test"
+    x, x_all = bb.sample_iadb_conditional(ToyCond(6), x0, xc, 100, (0.2, 0.0, 3.0))
+    want, wall = osam.sample_iadb_conditional(ToyCond(6), x0.cpu(), xc.cpu(), 100, (0.2, 0.0, 3.0), osam.make_opt())
+    assert torch.equal(x.cpu(), want) and len(x_all) == len(wall)
+
+
+@pytest.mark.parametrize("oc,nt", [(8, "gaussianBN"), (4, "gaussianBN"), (4, "gaussian")])
+def test_latent_scheduler_and_loop(oc, nt):
+    x = torch.randn(3, 4, 16, 16, device=DEV)
+    d = torch.randn(3, oc, 16, 16, device=DEV)
+    sch = bb.IADBScheduler(noise_type=nt, out_channels=oc)
+    with pytest.raises(ValueError):
+        sch.step(d, 3, x)
+    sch.set_timesteps(250)
+    got = sch.step(d, 17, x)
+    want = osam.iadb_scheduler_step(d.cpu(), 17, x.cpu(), 250, nt, oc)
+    assert torch.equal(got.cpu(), want)
+    for g_ in (False, True):
+        y = bb.sample_latent_iadb(ToyEps(oc), x, 50, nt, oc, use_graph=g_)
+        assert torch.equal(y.cpu(), osam.latent_loop(ToyEps(oc), x.cpu(), 50, nt, oc))
+
+
+@pytest.mark.parametrize("eta", [0.0, 1.0, 0.3])
+@pytest.mark.parametrize("n", [100, 37])
+def test_ddim_step_and_loop_vs_oracle(eta, n):
+    tables = osam.DDIMTables()
+    tables.set_timesteps(n)
+    sch = bb.DDIMScheduler()
+    sch.set_timesteps(n)
+    x = torch.randn(4, 3, 16, 16, device=DEV) * 2
+    eps = torch.randn(4, 3, 16, 16, device=DEV)
+    vn = torch.randn(4, 3, 16, 16, device=DEV)
+    for t in (int(sch.timesteps[0]), int(sch.timesteps[n // 2]), 0):
+        got = sch.step(eps, t, x, eta=eta, variance_noise=vn).prev_sample
+        want = osam.ddim_step(tables, eps.cpu(), t, x.cpu(), eta, vn.cpu())
+        np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
+        assert (got.cpu() - want).abs().max().item() <= 2e-6          # in practice <= 1-2 ulp
+    noise_bank = torch.randn(n, 4, 3, 16, 16)
+    fn_gpu = lambda i, t, xx: noise_bank[i].to(DEV)
+    fn_cpu = lambda i, t, xx: noise_bank[i]
+    got = sample_ddim(ToyEps(3), x, n, eta=eta, noise_fn=fn_gpu)
+    want = osam.ddim_loop(ToyEps(3), x.cpu(), n, eta=eta, noise_fn=fn_cpu)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
+    if eta == 0:
+        gg = sample_ddim(ToyEps(3), x, n, use_graph=True)
+        assert torch.equal(gg, got)
+
+
+def test_ddim_with_time_varying_blue_noise(L_np):
+    """BASELINE config 3: eta > 0, variance noise = get_noise_v2('gaussianBN', gamma(t))."""
+    from oracle import noise as on
+    L = torch.from_numpy(L_np).to(DEV)
+    n, B = 10, 2
+    x = torch.randn(B, 3, 64, 64, device=DEV)
+    bank = torch.randn(n, B, 3, 64, 64)
+    gam = torch.linspace(1, 0, n)
+
+    def fn_gpu(i, t, xx):
+        g = torch.full((B,), float(gam[i]), device=DEV)
+        return bb.get_noise_v2(DEV, bank[i].to(DEV), L, g, t, "gaussianBN", "test", True)[0]
+
+    def fn_cpu(i, t, xx):
+        g = np.full((B,), float(gam[i]), np.float32)
+        return torch.from_numpy(on.get_noise_np(bank[i].numpy(), L_np, g, "gaussianBN", "test", True)[0])
+    got = sample_ddim(ToyEps(3), x, n, eta=1.0, noise_fn=fn_gpu)
+    want = osam.ddim_loop(ToyEps(3), x.cpu(), n, eta=1.0, noise_fn=fn_cpu)
+    np.testing.assert_allclose(got.cpu().numpy(), want.numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_to_uint8_nhwc():
+    from bndm_b200.io import to_uint8_nhwc
+    x = torch.randn(3, 3, 16, 16, device=DEV) * 1.5
+    got = to_uint8_nhwc(x)
+    want = ((x / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1) * 255).round().to(torch.uint8)   # ddim_diffusers.py:687-688
+    assert got.dtype == torch.uint8 and torch.equal(got, want)
+
+
+def test_full_size_unet_sampling_graph_equals_eager_short():
+    """Config-2 shaped run (64^2, out_channel 6, real UNet) for a few steps: the CUDA-graph path
+    must reproduce the eager path exactly (same kernels, same order)."""
+    from bndm_b200.unet import get_model
+    torch.manual_seed(0)
+    model = get_model(3, 6, 64).to(DEV).eval()
+    x0 = torch.randn(2, 3, 64, 64, device=DEV)
+    a = bb.sample_iadb(model, x0, 4, "sigmoid", (1000.0, 0.0, 3.0), 6, "gaussianBN", "train")
+    b = bb.sample_iadb(model, x0, 4, "sigmoid", (1000.0, 0.0, 3.0), 6, "gaussianBN", "train", use_graph=True)
+    assert torch.isfinite(a).all()
+    np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    # and the oracle loop with the SAME module on the same device (parity ladder step 3)
+    c = osam.sample_iadb_utils(model, x0, 4, "sigmoid", (1000.0, 0.0, 3.0), 6, "gaussianBN", "train")
+    np.testing.assert_allclose(a.cpu().numpy(), c.cpu().numpy(), rtol=1e-4, atol=1e-5)
