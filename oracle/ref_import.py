@@ -10,6 +10,7 @@ so empty stand-in modules are inserted into ``sys.modules`` before the import.
 from __future__ import annotations
 
 import importlib
+import importlib.util
 import os
 import sys
 import types
@@ -43,18 +44,20 @@ def load_reference():
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     _stub("diffusers", UNet2DModel=type("UNet2DModel", (), {}))
 
-    # our repo also ships a `bluenoise` shim package; make sure the reference's wins here
-    saved = {k: sys.modules.pop(k) for k in list(sys.modules)
-             if k == "bluenoise" or k.startswith("bluenoise.") or k == "utils"}
-    sys.path.insert(0, REFERENCE_ROOT)
+    # The reference's bluenoise/ has no __init__.py (a namespace package) while this repo ships a
+    # regular `bluenoise` shim package, which would win any path-based import: load by file path.
+    def _by_path(name, path):
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    saved_utils = sys.modules.pop("utils", None)
     try:
-        gnr = importlib.import_module("bluenoise.get_noise_recent")
-        ref_utils = importlib.import_module("utils")
+        gnr = _by_path("_bndm_reference_get_noise_recent", os.path.join(REFERENCE_ROOT, "bluenoise", "get_noise_recent.py"))
+        ref_utils = _by_path("_bndm_reference_utils", os.path.join(REFERENCE_ROOT, "utils.py"))
     finally:
-        sys.path.remove(REFERENCE_ROOT)
-        for k in list(sys.modules):
-            if k == "bluenoise" or k.startswith("bluenoise.") or k == "utils":
-                sys.modules.pop(k)
-        sys.modules.update(saved)
+        if saved_utils is not None:
+            sys.modules["utils"] = saved_utils
     assert gnr.__file__.startswith(REFERENCE_ROOT), gnr.__file__
     return gnr.get_noise_v2, gnr.noise_padding, ref_utils

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, load_golden, assert_golden
 
 HEADER = os.path.join(ROOT, "include", "bndm_b200.h")
 
@@ -71,7 +71,7 @@ def test_schedule_functions_match_golden():
         else:
             p = (float(parts[2][3:]), float(parts[3][1:]), float(parts[4][1:]))
             got = get_scheduler_gamma(x, parts[1], p, T)
-        assert np.array_equal(got.numpy(), g[key]), key
+        assert_golden(got.numpy(), g[key], key)
 
 
 def test_iadb_table_rows_are_the_reference_differences():

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ATOL, NOISE_GOLDENS, RTOL, SAMPLER_GOLDENS, load_golden
+from conftest import ATOL, NOISE_GOLDENS, RTOL, SAMPLER_GOLDENS, assert_golden, load_golden
 from oracle import noise as on
 from oracle import sampler as osam
 from oracle import schedules as osch
@@ -48,7 +48,7 @@ def test_schedules_match_golden():
             kind = parts[1]
             p = (float(parts[2][3:]), float(parts[3][1:]), float(parts[4][1:]))
             got = osch.gamma_schedule(x, kind, p, T)
-        assert np.array_equal(got.numpy(), g[key]), key
+        assert_golden(got.numpy(), g[key], key)
 
 
 @pytest.mark.parametrize("name", SAMPLER_GOLDENS)
@@ -58,9 +58,9 @@ def test_sampler_matches_golden_bitwise(name):
     x, snaps, _ = osam.sample_iadb_utils(ToyEps(oc), torch.from_numpy(g["x0"].copy()), T, "sigmoid",
                                          tuple(g["scheduler_params"]), oc, nt, "test")
     assert len(snaps) == int(g["n_snaps"])
-    assert np.array_equal(x.numpy(), g["x"])
+    assert_golden(x.numpy(), g["x"], name)
     for i, idx in enumerate(g["snap_idx"]):
-        assert np.array_equal(snaps[int(idx)].numpy(), g["snaps"][i])
+        assert_golden(snaps[int(idx)].numpy(), g["snaps"][i], name)
 
 
 def test_opt_variant_shares_arithmetic_with_utils():
