@@ -20,6 +20,7 @@ captured graph serves all T steps.
 from __future__ import annotations
 
 import time
+import weakref
 from types import SimpleNamespace
 
 import numpy as np
@@ -91,65 +92,164 @@ def iadb_step(x, d, dalpha, dgamma=None, out=None):
 
 
 class GraphedStep:
-    """[d = model(x, t_vec); K2(x, d)] captured once for a fixed shape and replayed per step.
-    x, t_vec and the step counter are static device buffers the graph reads and writes."""
+    """One sampling step for a fixed shape, captured once and replayed per step; x, t_vec and
+    the step counter are static device buffers the graph reads and writes.
 
-    def __init__(self, model_call, stepper: IadbStepper, x_static: torch.Tensor, warmup: int = 2):
+    fused=True   graph = [d = model(x, t_vec); K2(x, d)]            (one replay per step)
+    fused=False  graph = [d = model(x, t_vec)], K2 launched eagerly after each replay on the
+                 same stream -- lets a caller bracket K2 with CUDA events (bench.py's live
+                 roofline measurement); same kernels, same order, same results."""
+
+    def __init__(self, model_call, stepper: IadbStepper, x_static: torch.Tensor, warmup: int = 2, fused: bool = True):
         self.stepper = stepper
         self.x = x_static
+        self.fused = fused
+        self.d = None
         self.graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream(device=x_static.device)
-        side.wait_stream(torch.cuda.current_stream(x_static.device))
+        dev = x_static.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
         keep = x_static.clone()
         with torch.cuda.stream(side):
             for _ in range(warmup):                       # lazy inits (cuDNN plans, workspaces) outside capture
                 stepper.step_(x_static, model_call(x_static, stepper.t_vec))
-        torch.cuda.current_stream(x_static.device).wait_stream(side)
+        torch.cuda.current_stream(dev).wait_stream(side)
         x_static.copy_(keep)
         stepper.reset()
         with torch.cuda.graph(self.graph, stream=side):
-            stepper.step_(x_static, model_call(x_static, stepper.t_vec))
+            d = _lib.require_cuda_f32(model_call(x_static, stepper.t_vec), "model output")
+            if fused:
+                stepper.step_(x_static, d)
+            else:
+                self.d = d
         stepper.reset()
 
-    def replay(self):
+    def replay(self, events=None):
         self.graph.replay()
+        if not self.fused:
+            if events is not None:
+                events[0].record()
+            self.stepper.step_(self.x, self.d)
+            if events is not None:
+                events[1].record()
 
 
 def _call_model_iadb(model):
     return lambda x, t: model(x, t, return_dict=False)[0]
 
 
-@torch.no_grad()
+class IadbSampler:
+    """A sampling run of fixed shape and schedule, set up once and callable many times: the
+    coefficient table, the device-side step state, the static x buffer and (optionally) the
+    captured [UNet -> K2] graph all persist across calls.  ``sample_iadb(..., use_graph=True)``
+    keeps one of these per (model, shape, schedule).
+
+    graph: None (eager), 'step' (UNet+K2 in one graph) or 'unet' (UNet graph + eager K2).
+    time_step_kernel: record a CUDA event pair around every K2 launch (graph must not be 'step');
+    ``step_kernel_ms()`` then returns the per-launch durations of the last run."""
+
+    def __init__(self, model, shape, nb_step, scheduler_gamma="sigmoid", scheduler_params=(1000.0, 0.0, 3.0),
+                 out_channel=6, noise_type="gaussianBN", scheduler_alpha="linear", alpha_param=1000.0, x_c=None,
+                 device="cuda", graph="step", time_step_kernel=False, table=None, first_t=None):
+        self.device = torch.device(device)
+        self.shape = tuple(shape)
+        B, C = self.shape[0], self.shape[1]
+        self.nb_step = nb_step
+        if table is None:
+            _expected_out_channels(noise_type, out_channel, C)
+            table, first_t = iadb_table(nb_step, scheduler_alpha, scheduler_gamma,
+                                        tuple(float(p) for p in scheduler_params), alpha_param)
+        else:
+            table = table.clone()
+        if not (noise_type in TWO_HEAD and out_channel == 2 * C):
+            table[:, 1] = 0.0
+        self.stepper = IadbStepper(table, first_t, B, self.device)
+        self.x = torch.zeros(self.shape, dtype=torch.float32, device=self.device)
+        call = _call_model_iadb(model)
+        if x_c is not None:
+            x_c = _lib.require_cuda_f32(x_c, "x_c")
+            inner = call
+            call = lambda xx, tt: inner(torch.cat([xx, x_c], 1), tt)          # iadb_bn.py:406
+        self.call = call
+        try:
+            self._model_ref = weakref.ref(model)
+        except TypeError:
+            self._model_ref = lambda: model
+        if time_step_kernel and graph == "step":
+            raise ValueError("time_step_kernel needs graph in (None, 'unet')")
+        self.graphed = None
+        if graph is not None:
+            with torch.no_grad():
+                self.graphed = GraphedStep(call, self.stepper, self.x, fused=(graph == "step"))
+        self.events = None
+        if time_step_kernel:
+            self.events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                           for _ in range(nb_step)]
+        self.kernel_launches_per_run = nb_step            # K2 launches of one run (graph nodes count)
+
+    @torch.no_grad()
+    def run(self, x0, on_step=None):
+        """x0 is copied into the static buffer (the reference never writes into x0,
+        iadb_bn.py:326 makes new tensors); returns the static buffer (clone it to keep it)."""
+        self.x.copy_(_lib.require_cuda_f32(x0, "x0"))
+        self.stepper.reset()
+        for i, t in enumerate(reversed(range(self.nb_step))):
+            ev = self.events[i] if self.events is not None else None
+            if self.graphed is not None:
+                self.graphed.replay(ev)
+            else:
+                d = self.call(self.x, self.stepper.t_vec)
+                if ev is not None:
+                    ev[0].record()
+                self.stepper.step_(self.x, d)
+                if ev is not None:
+                    ev[1].record()
+            if on_step is not None:
+                on_step(t, self.x)
+        return self.x
+
+    def __call__(self, x0):
+        return self.run(x0).clone()
+
+    def step_kernel_ms(self):
+        """Per-launch K2 durations (ms) of the last run; synchronises on the last event."""
+        if self.events is None:
+            raise ValueError("constructed without time_step_kernel")
+        self.events[-1][1].synchronize()
+        return [a.elapsed_time(b) for a, b in self.events]
+
+
+_sampler_cache: "dict[tuple, IadbSampler]" = {}
+
+
 def _run_iadb(model, x0, x_c, nb_step, scheduler_alpha, scheduler_gamma, scheduler_params, out_channel, noise_type,
               train_or_test, log_freq, use_graph, alpha_param=1000.0):
     x0 = _lib.require_cuda_f32(x0, "x0")
-    B, C = x0.shape[0], x0.shape[1]
-    _expected_out_channels(noise_type, out_channel, C)
-    table, first_t = iadb_table(nb_step, scheduler_alpha, scheduler_gamma, tuple(float(p) for p in scheduler_params),
-                                alpha_param)
-    if not (noise_type in TWO_HEAD and out_channel == 2 * C):
-        table[:, 1] = 0.0
-    stepper = IadbStepper(table, first_t, B, x0.device)
-    x = x0.clone()                      # the reference never writes into x0 (iadb_bn.py:326 makes new tensors)
-    call = _call_model_iadb(model)
-    if x_c is not None:
-        x_c = _lib.require_cuda_f32(x_c, "x_c")
-        inner = call
-        call = lambda xx, tt: inner(torch.cat([xx, x_c], 1), tt)          # iadb_bn.py:406
+    params = tuple(float(p) for p in scheduler_params)
+    key = (id(model), tuple(x0.shape), str(x0.device), nb_step, scheduler_alpha, scheduler_gamma, params, out_channel,
+           noise_type, float(alpha_param), None if x_c is None else x_c.data_ptr())
+    sampler = _sampler_cache.get(key) if use_graph else None
+    if sampler is not None and sampler._model_ref() is not model:      # id() reuse after garbage collection
+        sampler = None
+    if sampler is None:
+        sampler = IadbSampler(model, x0.shape, nb_step, scheduler_gamma, params, out_channel, noise_type,
+                              scheduler_alpha, alpha_param, x_c, x0.device, graph="step" if use_graph else None)
+        if use_graph:
+            if len(_sampler_cache) >= 4:
+                _sampler_cache.pop(next(iter(_sampler_cache)))
+            _sampler_cache[key] = sampler
     if nb_step == 1000:
         log_freq = 100
-    graphed = GraphedStep(call, stepper, x) if use_graph else None
 
     x_all, per_step = [], []
-    for t in reversed(range(nb_step)):
-        tic = time.time()
-        if graphed is not None:
-            graphed.replay()
-        else:
-            stepper.step_(x, call(x, stepper.t_vec))
-        per_step.append(time.time() - tic)
+    tic = [time.time()]
+
+    def on_step(t, x):
+        per_step.append(time.time() - tic[0])
         if train_or_test == "test" and (t % log_freq == 0 or t == nb_step - 1):
             x_all.append(x.clone())
+        tic[0] = time.time()
+    x = sampler.run(x0, on_step).clone()
     return x, x_all, per_step
 
 
@@ -228,17 +328,14 @@ class IADBScheduler:
 def sample_latent_iadb(model, noise, num_steps, noise_type="gaussianBN", out_channels=8, use_graph=False):
     """The latent sampling loop latent_iadb_bn_diffusers.py:524-534 (VAE decode left to the
     caller).  UNet timestep is alpha=(t+1)/N broadcast over the batch (:525-528)."""
-    x = _lib.require_cuda_f32(noise, "noise").clone()
-    B, C = x.shape[0], x.shape[1]
+    x = _lib.require_cuda_f32(noise, "noise")
+    C = x.shape[1]
+    if noise_type in TWO_HEAD:
+        if out_channels not in (C, 2 * C):
+            raise NotImplementedError
+    elif noise_type != "gaussian":
+        raise NotImplementedError
     table, first_t = latent_table(num_steps)
-    if not (noise_type in TWO_HEAD and out_channels == 2 * C):
-        table[:, 1] = 0.0
-    stepper = IadbStepper(table, first_t, B, x.device)
-    call = _call_model_iadb(model)
-    graphed = GraphedStep(call, stepper, x) if use_graph else None
-    for _ in range(num_steps):
-        if graphed is not None:
-            graphed.replay()
-        else:
-            stepper.step_(x, call(x, stepper.t_vec))
-    return x
+    sampler = IadbSampler(model, x.shape, num_steps, out_channel=out_channels, noise_type=noise_type, device=x.device,
+                          graph="step" if use_graph else None, table=table, first_t=first_t)
+    return sampler(x)
