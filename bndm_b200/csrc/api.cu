@@ -51,6 +51,7 @@ struct bndm_L {
   int sm100 = 0;
   // workspace (owned), sized for `cap_cols` padded columns
   int cap_cols = 0;
+  int req_cols = 0;             // max_columns the workspace was sized for
   size_t cap_partial = 0;
   float *z_raw = nullptr, *z_hi = nullptr, *z_lo = nullptr, *partials = nullptr;
   int64_t ws_bytes = 0;
@@ -60,15 +61,15 @@ struct bndm_L {
   int ev_valid = 0;
 };
 
-static const int kUnitCap = 592;   // most partial tiles any schedule may produce per column block
+static const int kUnitCap = 592;   // most partial tiles a SIMT schedule may produce per column block
 
 static int pad_cols(int n_cols) {
   const int nb = tc_pick_nb(n_cols);
   return (n_cols + nb - 1) / nb * nb;
 }
 
-// Chunk length of the split-K schedule: enough units to fill the 148 SMs for the given
-// number of column blocks, never more than kUnitCap partial tiles.
+// SIMT reference path: chunk length of the split-K schedule (enough units to fill the SMs for
+// the given number of column blocks, never more than kUnitCap partial tiles).
 static Schedule pick_schedule(int n_row_tiles, int dense, int col_blocks) {
   Schedule s;
   s.n_row_tiles = n_row_tiles;
@@ -81,18 +82,21 @@ static Schedule pick_schedule(int n_row_tiles, int dense, int col_blocks) {
   return s;
 }
 
-// fp32 elements of partial-tile workspace a call with n_cols columns may need (any branch)
+// fp32 elements of partial-tile workspace a call with n_cols columns may need (any branch,
+// either contraction kernel)
 static size_t partial_elems(int n_cols) {
   const int cp = pad_cols(n_cols);
   const int nb = tc_pick_nb(n_cols);
   size_t worst = 0;
   for (int dense = 0; dense < 2; ++dense)
-    for (int rows = kNumBlk / 2; rows <= kNumBlk; rows += kNumBlk / 2)
-      for (int simt = 0; simt < 2; ++simt) {
-        const Schedule s = pick_schedule(rows, dense, simt ? (cp + 63) / 64 : cp / nb);
-        const size_t e = (size_t)s.n_units() * cp * kBlk;
-        if (e > worst) worst = e;
-      }
+    for (int rows = kNumBlk / 2; rows <= kNumBlk; rows += kNumBlk / 2) {
+      const Schedule s = pick_schedule(rows, dense, (cp + 63) / 64);
+      const size_t e_simt = (size_t)s.n_units() * cp * kBlk;
+      const StreamK k = make_streamk(rows, dense, cp / nb, tc_num_sms());
+      const size_t e_tc = (size_t)k.n_slots() * nb * kBlk;
+      if (e_simt > worst) worst = e_simt;
+      if (e_tc > worst) worst = e_tc;
+    }
   return worst;
 }
 
@@ -103,6 +107,7 @@ static void free_ws(bndm_L *h) {
   cudaFree(h->partials);
   h->z_raw = h->z_hi = h->z_lo = h->partials = nullptr;
   h->cap_cols = 0;
+  h->req_cols = 0;
   h->cap_partial = 0;
   h->ws_bytes = 0;
 }
@@ -110,16 +115,24 @@ static void free_ws(bndm_L *h) {
 static int alloc_ws(bndm_L *h, int max_columns) {
   free_ws(h);
   const int cols_pad = pad_cols(max_columns);
-  size_t pe = partial_elems(max_columns);
-  // smaller calls pick finer schedules: cover every single-column-block configuration too
-  const size_t small = (size_t)kUnitCap * (cols_pad < 256 ? cols_pad : 256) * kBlk;
-  if (small > pe) pe = small;
+  size_t pe = 0;
+  // a smaller call may pick a finer schedule / another column blocking: size for the worst of
+  // every column count up to the requested one (cheap: a few hundred evaluations)
+  for (int n = 1; n <= max_columns; n = (n < 16 ? n + 1 : n + 16)) {
+    const size_t e = partial_elems(n);
+    if (e > pe) pe = e;
+  }
+  {
+    const size_t e = partial_elems(max_columns);
+    if (e > pe) pe = e;
+  }
   const size_t zb = (size_t)cols_pad * kNPix * sizeof(float);
   CK(cudaMalloc(&h->z_raw, zb));
   CK(cudaMalloc(&h->z_hi, zb));
   CK(cudaMalloc(&h->z_lo, zb));
   CK(cudaMalloc(&h->partials, pe * sizeof(float)));
   h->cap_cols = cols_pad;
+  h->req_cols = max_columns;
   h->cap_partial = pe;
   h->ws_bytes = (int64_t)(3 * zb + pe * sizeof(float));
   return BNDM_OK;
@@ -175,7 +188,7 @@ int bndm_prepare_L(const float *L_dev, int n, int max_columns, void *stream, bnd
 
 int bndm_reserve_columns(bndm_L *h, int max_columns, void *stream) {
   if (!h) { set_error("null handle"); return BNDM_ERR_ARG; }
-  if (pad_cols(max_columns) <= h->cap_cols && partial_elems(max_columns) <= h->cap_partial) return BNDM_OK;
+  if (max_columns <= h->req_cols) return BNDM_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (stream_is_capturing(s)) { set_error("workspace growth requested during stream capture"); return BNDM_ERR_WORKSPACE; }
   CK(cudaStreamSynchronize(s));
@@ -234,10 +247,17 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
   const int n_cols = B * C * (mode == kRes128 ? 4 : 1);
   const int nb = tc_pick_nb(n_cols);
   const int n_cols_pad = (n_cols + nb - 1) / nb * nb;
-  const Schedule sched = pick_schedule(mode == kRes32 ? kNumBlk / 2 : kNumBlk, dense, simt ? (n_cols_pad + 63) / 64 : n_cols_pad / nb);
-  if (n_cols_pad > h->cap_cols || (size_t)sched.n_units() * n_cols_pad * kBlk > h->cap_partial) {
-    int rc = bndm_reserve_columns(h, n_cols, stream);
+  const int n_row_tiles = mode == kRes32 ? kNumBlk / 2 : kNumBlk;
+  const Schedule sched = pick_schedule(n_row_tiles, dense, (n_cols_pad + 63) / 64);          // SIMT path
+  const StreamK sk = make_streamk(n_row_tiles, dense, n_cols_pad / nb, tc_num_sms());         // tcgen05 path
+  const size_t need = simt ? (size_t)sched.n_units() * n_cols_pad * kBlk : (size_t)sk.n_slots() * nb * kBlk;
+  if (n_cols_pad > h->cap_cols || need > h->cap_partial) {
+    int rc = bndm_reserve_columns(h, n_cols > h->req_cols ? n_cols : h->req_cols + 1, stream);
     if (rc != BNDM_OK) return rc;
+    if (n_cols_pad > h->cap_cols || need > h->cap_partial) {
+      set_error("internal: workspace still too small after growth (cols %d, partial %zu)", n_cols_pad, need);
+      return BNDM_ERR_WORKSPACE;
+    }
   }
 
   // K1a: the white columns are already in GEMM order unless they are gathered from an image;
@@ -261,8 +281,8 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
   if (prof) CK(cudaEventRecord(h->ev[1], s));
   const float *z_cols = need_raw ? h->z_raw : z;
 
-  // K1b: split-K triangular contraction -> partial tiles
   if (simt) {
+    // K1b (fp32 FFMA reference kernel): split-K partial tiles, then ordered combine + lerp + layout
     GemmArgs g;
     g.L = h->L;
     g.z = z_cols;
@@ -270,7 +290,23 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
     g.n_cols_pad = n_cols_pad;
     g.sched = sched;
     CK(launch_gemm_simt(g, s));
+    if (prof) CK(cudaEventRecord(h->ev[2], s));
+    EpilogueArgs ep;
+    ep.partials = h->partials;
+    ep.z_cols = z_cols;
+    ep.gamma = gamma;
+    ep.out = out;
+    ep.out_bn = out_bn;
+    ep.out_wn = out_wn;
+    ep.n_cols = n_cols;
+    ep.n_cols_pad = n_cols_pad;
+    ep.B = B;
+    ep.C = C;
+    ep.res_mode = mode;
+    ep.sched = sched;
+    CK(launch_epilogue(ep, s));
   } else {
+    // K1b (tcgen05, persistent stream-K) -> K1c (ordered combine + lerp + layout)
     TcGemmArgs g;
     g.L_hi = h->L_hi;
     g.L_lo = h->L_lo;
@@ -279,26 +315,24 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
     g.partials = h->partials;
     g.n_cols_pad = n_cols_pad;
     g.nb = nb;
-    g.sched = sched;
+    g.sk = sk;
     CK(launch_gemm_tc(g, s));
+    if (prof) CK(cudaEventRecord(h->ev[2], s));
+    CombineArgs cb;
+    cb.partials = h->partials;
+    cb.z_cols = z_cols;
+    cb.gamma = gamma;
+    cb.out = out;
+    cb.out_bn = out_bn;
+    cb.out_wn = out_wn;
+    cb.n_cols = n_cols;
+    cb.nb = nb;
+    cb.B = B;
+    cb.C = C;
+    cb.res_mode = mode;
+    cb.sk = sk;
+    CK(launch_combine(cb, s));
   }
-
-  if (prof) CK(cudaEventRecord(h->ev[2], s));
-  // K1c: ordered combine + lerp + layout
-  EpilogueArgs ep;
-  ep.partials = h->partials;
-  ep.z_cols = z_cols;
-  ep.gamma = gamma;
-  ep.out = out;
-  ep.out_bn = out_bn;
-  ep.out_wn = out_wn;
-  ep.n_cols = n_cols;
-  ep.n_cols_pad = n_cols_pad;
-  ep.B = B;
-  ep.C = C;
-  ep.res_mode = mode;
-  ep.sched = sched;
-  CK(launch_epilogue(ep, s));
   if (prof) {
     CK(cudaEventRecord(h->ev[3], s));
     h->ev_valid = 1;
@@ -349,6 +383,55 @@ int bndm_ddim_step_f32(float *x_out, const float *x, const float *eps, const flo
   DdimArgs a{x_out, x, eps, noise, coef, state, t_next_out, B, clip, n};
   CK(launch_ddim_step(a, (cudaStream_t)stream));
   return BNDM_OK;
+}
+
+// Host-only self-check of the stream-K schedule (used by the CPU test-suite): every stage is
+// covered exactly once, segment slots are unique and below n_slots(), and the slot range the
+// combine kernel derives for a row tile is exactly the set of segments the GEMM writes for it.
+int bndm_debug_streamk_check(int n_tiles, int dense, int n_colblk, int num_sms) {
+  const StreamK k = make_streamk(n_tiles, dense, n_colblk, num_sms);
+  if (k.G < 1 || k.G > num_sms || k.W != n_colblk * k.Stot) { set_error("streamk: bad G/W"); return BNDM_ERR_ARG; }
+  const int ns = k.n_slots();
+  int *owner = new int[ns];
+  int *tile_of = new int[ns];
+  for (int i = 0; i < ns; ++i) owner[i] = tile_of[i] = -1;
+  int rc = BNDM_OK;
+  int covered = 0;
+  for (int c = 0; c < k.G && rc == BNDM_OK; ++c) {
+    const int b = k.cta_begin(c), e = k.cta_begin(c + 1);
+    if (e <= b) { set_error("streamk: empty range for cta %d", c); rc = BNDM_ERR_ARG; break; }
+    if (c == 0 && b != 0) { set_error("streamk: range does not start at 0"); rc = BNDM_ERR_ARG; break; }
+    for (int g = b; g < e;) {
+      int cb, tile, s0;
+      k.decode(g, cb, tile, s0);
+      if (cb < 0 || cb >= n_colblk || tile < 0 || tile >= n_tiles || k.tile_begin(cb, tile) + s0 != g) {
+        set_error("streamk: decode(%d) inconsistent", g); rc = BNDM_ERR_ARG; break;
+      }
+      const int se = e < k.tile_end(cb, tile) ? e : k.tile_end(cb, tile);
+      if (k.cta_of(g) != c || k.cta_of(se - 1) != c) { set_error("streamk: cta_of mismatch at %d", g); rc = BNDM_ERR_ARG; break; }
+      const int sl = k.slot(c, cb, tile);
+      if (sl < 0 || sl >= ns || owner[sl] != -1) { set_error("streamk: slot %d reused/out of range", sl); rc = BNDM_ERR_ARG; break; }
+      owner[sl] = c;
+      tile_of[sl] = cb * n_tiles + tile;
+      covered += se - g;
+      g = se;
+    }
+  }
+  if (rc == BNDM_OK && (covered != k.W || k.cta_begin(k.G) != k.W)) { set_error("streamk: covered %d of %d", covered, k.W); rc = BNDM_ERR_ARG; }
+  for (int cb = 0; cb < n_colblk && rc == BNDM_OK; ++cb)
+    for (int t = 0; t < n_tiles && rc == BNDM_OK; ++t) {
+      const int c0 = k.cta_of(k.tile_begin(cb, t)), c1 = k.cta_of(k.tile_end(cb, t) - 1);
+      int count = 0;
+      for (int sl = 0; sl < ns; ++sl) count += tile_of[sl] == cb * n_tiles + t;
+      if (count != c1 - c0 + 1) { set_error("streamk: tile (%d,%d) has %d segments, combine expects %d", cb, t, count, c1 - c0 + 1); rc = BNDM_ERR_ARG; }
+      for (int c = c0; c <= c1 && rc == BNDM_OK; ++c)
+        if (tile_of[k.slot(c, cb, t)] != cb * n_tiles + t || owner[k.slot(c, cb, t)] != c) {
+          set_error("streamk: slot of cta %d for tile (%d,%d) not written by it", c, cb, t); rc = BNDM_ERR_ARG;
+        }
+    }
+  delete[] owner;
+  delete[] tile_of;
+  return rc;
 }
 
 int bndm_to_uint8_nhwc(const float *x, uint8_t *out, int B, int C, int H, int W, void *stream) {

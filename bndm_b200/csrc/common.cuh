@@ -9,6 +9,7 @@ constexpr int kTile = 64;            // blue-noise tile edge
 constexpr int kNPix = kTile * kTile; // 4096 = M = K of the contraction
 constexpr int kBlk = 128;            // row-tile / k-block edge of the triangular schedule
 constexpr int kNumBlk = kNPix / kBlk;
+constexpr int kStageK = 32;          // k extent of one tensor-core pipeline stage (128-byte rows)
 
 // Output mapping of GEMM column j / row p (see DESIGN.md "K1 addressing")
 enum ResMode : int { kRes64 = 0, kRes32 = 1, kRes128 = 2 };
@@ -81,18 +82,70 @@ cudaError_t launch_white128(const float *x, float *out, int B, int C, cudaStream
 cudaError_t launch_split_tf32(const float *src, float *hi, float *lo, int64_t n, cudaStream_t s);
 cudaError_t launch_tri_check(const float *L, int n, int *flag_dev, cudaStream_t s);
 
-// tcgen05 path: opaque per-handle state lives in noise_gemm_tc.cu
-struct TcPlan;
+// ---- stream-K schedule of the tensor-core contraction (see noise_gemm_tc.cu) ---------------
+// Stage = (row tile, 32 k values, column block).  Row tile i owns 4 (i + 1) stages (lower-
+// triangular L) or 128 (dense); the W stages of all column blocks are cut into G contiguous
+// equal ranges, one per CTA.  Shared by the GEMM kernel and the combine kernel.
+struct StreamK {
+  int n_tiles;    // row tiles: 32, or 16 for the 32^2 branch (rows with h >= 32 are never stored)
+  int dense;      // 0: lower-triangular, 1: dense
+  int n_colblk;   // column blocks of nb columns
+  int G;          // CTAs = min(#SMs, W)
+  int Stot;       // stages per column block
+  int W;          // n_colblk * Stot
+  __host__ __device__ int cum(int i) const { return dense ? (kNPix / kStageK) * i : 2 * i * (i + 1); }
+  __host__ __device__ int cta_begin(int c) const { return (int)((int64_t)c * W / G); }
+  __host__ __device__ int cta_of(int g) const { return (int)((((int64_t)g + 1) * G - 1) / W); }
+  __host__ __device__ int tile_begin(int cb, int tile) const { return cb * Stot + cum(tile); }
+  __host__ __device__ int tile_end(int cb, int tile) const { return cb * Stot + cum(tile + 1); }
+  __host__ __device__ void decode(int g, int &cb, int &tile, int &s) const {
+    cb = g / Stot;
+    const int r = g - cb * Stot;
+    int i = 0;
+    while (cum(i + 1) <= r) ++i;
+    tile = i;
+    s = r - cum(i);
+  }
+  // partial-tile slot of the segment CTA `cta` computes inside (cb, tile): cta + tile index is
+  // strictly increasing along the global stage order, hence unique per segment
+  __host__ __device__ int slot(int cta, int cb, int tile) const { return cta + cb * n_tiles + tile; }
+  __host__ __device__ int n_slots() const { return G + n_colblk * n_tiles - 1; }
+};
+inline StreamK make_streamk(int n_tiles, int dense, int n_colblk, int num_sms) {
+  StreamK k;
+  k.n_tiles = n_tiles;
+  k.dense = dense;
+  k.n_colblk = n_colblk;
+  k.Stot = k.cum(n_tiles);
+  k.W = n_colblk * k.Stot;
+  k.G = num_sms < k.W ? num_sms : k.W;
+  return k;
+}
+
 struct TcGemmArgs {
   const float *L_hi, *L_lo;   // [4096][4096] tf32-split copies of L
   const float *z_hi, *z_lo;   // [n_cols_pad][4096]
-  float *partials;
-  int n_cols_pad;             // multiple of the column block nb
-  int nb;                     // columns per CTA (multiple of 16, <= 256)
-  Schedule sched;
+  float *partials;            // [n_slots][nb][128]
+  int n_cols_pad;             // n_colblk * nb
+  int nb;                     // columns per column block (multiple of 16, <= 256)
+  StreamK sk;
 };
 cudaError_t launch_gemm_tc(const TcGemmArgs &a, cudaStream_t s);
 int tc_pick_nb(int n_cols);   // column block for a given column count
+int tc_num_sms();
+
+// combine of the stream-K partials + everything get_noise_v2 does after the matmul
+struct CombineArgs {
+  const float *partials;   // [n_slots][nb][128]
+  const float *z_cols;     // packed raw columns [.][4096] (white values)
+  const float *gamma;      // [B] or null
+  float *out, *out_bn, *out_wn;
+  int n_cols, nb;
+  int B, C;
+  int res_mode;
+  StreamK sk;
+};
+cudaError_t launch_combine(const CombineArgs &a, cudaStream_t s);
 
 struct IadbArgs {
   float *x_out;

@@ -1,69 +1,129 @@
-// K1c "epilogue": deterministic split-K combine + everything get_noise_v2 does after the
+// K1c "combine": deterministic split-K combine + everything get_noise_v2 does after the
 // matmul (get_noise_recent.py:88-99, :113-118, :146-162): transpose back to NCHW, the
 // white<->blue lerp with per-sample gamma, the 32^2 crop, the 128^2 tile placement
 // (noise_padding :7-19) and the 128^2 noise_wn re-interpretation (:143-144).
 //
-// Partials: [unit][column][128 rows]; the units of row tile i are summed in ascending
-// k order by one thread => bit-reproducible run to run (no atomics).
+// Two front ends share one output mapping:
+//   combine_kernel   partials of the stream-K tensor-core contraction, [slot][column][128 rows];
+//                    the segments of a row tile are summed in ascending k order in fp32
+//   epilogue_kernel  partials of the SIMT reference contraction, [unit][column][128 rows]
+// Both are bit-reproducible run to run (fixed order, no atomics).
 #include "common.cuh"
 
 namespace bndm {
 
-constexpr int kColsPerBlock = 4;
+struct OutMap {
+  const float *z_cols;
+  const float *gamma;
+  float *out, *out_bn, *out_wn;
+  int B, C, res_mode;
+};
 
-__global__ void __launch_bounds__(128) epilogue_kernel(EpilogueArgs a) {
-  const int i = blockIdx.x;                 // row tile
-  const int r = threadIdx.x;                // row inside the tile
-  const int p = i * kBlk + r;               // pixel h*64 + w
+// Writes 4 consecutive pixels p..p+3 (same image row: p % 4 == 0) of GEMM column j.
+__device__ __forceinline__ void emit4(const OutMap &m, int j, int p, float4 bn) {
   const int h = p >> 6, w = p & 63;
+  int64_t dst;
+  float4 wn;
+  int b;
+  if (m.res_mode == kRes64) {
+    b = j / m.C;
+    dst = (int64_t)j * kNPix + p;
+    wn = *reinterpret_cast<const float4 *>(m.z_cols + (int64_t)j * kNPix + p);
+  } else if (m.res_mode == kRes32) {
+    if (h >= 32 || w >= 32) return;       // cropped away (:97-99)
+    b = j / m.C;
+    dst = (int64_t)j * 1024 + h * 32 + w;
+    wn = *reinterpret_cast<const float4 *>(m.z_cols + (int64_t)j * kNPix + p);
+  } else {
+    const int n = j / m.C, c = j - n * m.C;
+    b = n >> 2;                           // (4B,...) re-viewed as (B,4,...): n = 4 b' + k'
+    const int k = n & 3;
+    const int r0 = (k & 1) * kTile, c0 = (k >> 1) * kTile;     // noise_padding placement
+    dst = (((int64_t)b * m.C + c) * 128 + r0 + h) * 128 + c0 + w;
+    // (n, pixel, channel) memory re-read as (n, channel, pixel): flat f = c*4096 + p
+    const float *zn = m.z_cols + (int64_t)n * m.C * kNPix;
+    float t[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int f = c * kNPix + p + e;
+      const int cs = f % m.C, ps = f / m.C;
+      t[e] = zn[(int64_t)cs * kNPix + ps];
+    }
+    wn = make_float4(t[0], t[1], t[2], t[3]);
+  }
+  float4 o = bn;
+  if (m.gamma) {
+    const float g = m.gamma[b];
+    const float gi = __fsub_rn(1.0f, g);
+    o.x = __fadd_rn(__fmul_rn(bn.x, gi), __fmul_rn(wn.x, g));
+    o.y = __fadd_rn(__fmul_rn(bn.y, gi), __fmul_rn(wn.y, g));
+    o.z = __fadd_rn(__fmul_rn(bn.z, gi), __fmul_rn(wn.z, g));
+    o.w = __fadd_rn(__fmul_rn(bn.w, gi), __fmul_rn(wn.w, g));
+  }
+  *reinterpret_cast<float4 *>(m.out + dst) = o;
+  if (m.out_bn) *reinterpret_cast<float4 *>(m.out_bn + dst) = bn;
+  if (m.out_wn) *reinterpret_cast<float4 *>(m.out_wn + dst) = wn;
+}
+
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+}
+
+// ---- tensor-core path -----------------------------------------------------------------------
+// block = 32 row-quads x 8 columns; grid = (row tiles, ceil(n_cols / 8))
+constexpr int kCombCols = 8;
+
+__global__ void __launch_bounds__(256) combine_kernel(CombineArgs a) {
+  const int tile = blockIdx.x;
+  const int rq = threadIdx.x & 31;                 // rows 4 rq .. 4 rq + 3 of the tile
+  const int j = blockIdx.y * kCombCols + (threadIdx.x >> 5);
+  if (j >= a.n_cols) return;
+  const int cb = j / a.nb, jc = j - cb * a.nb;
+  const StreamK sk = a.sk;
+  const int c_first = sk.cta_of(sk.tile_begin(cb, tile));
+  const int c_last = sk.cta_of(sk.tile_end(cb, tile) - 1);
+  const int64_t slot_stride = (int64_t)a.nb * kBlk;
+  const float *P = a.partials + (int64_t)sk.slot(c_first, cb, tile) * slot_stride + (int64_t)jc * kBlk + rq * 4;
+  float4 bn = *reinterpret_cast<const float4 *>(P);
+  const int n = c_last - c_first;
+  int s = 1;
+  for (; s + 4 <= n + 1; s += 4) {                 // batches of 4 independent loads, summed in order
+    const float4 v0 = *reinterpret_cast<const float4 *>(P + (int64_t)s * slot_stride);
+    const float4 v1 = *reinterpret_cast<const float4 *>(P + (int64_t)(s + 1) * slot_stride);
+    const float4 v2 = *reinterpret_cast<const float4 *>(P + (int64_t)(s + 2) * slot_stride);
+    const float4 v3 = *reinterpret_cast<const float4 *>(P + (int64_t)(s + 3) * slot_stride);
+    bn = add4(add4(add4(add4(bn, v0), v1), v2), v3);
+  }
+  for (; s <= n; ++s) bn = add4(bn, *reinterpret_cast<const float4 *>(P + (int64_t)s * slot_stride));
+  const OutMap m{a.z_cols, a.gamma, a.out, a.out_bn, a.out_wn, a.B, a.C, a.res_mode};
+  emit4(m, j, tile * kBlk + rq * 4, bn);
+}
+
+cudaError_t launch_combine(const CombineArgs &a, cudaStream_t s) {
+  dim3 grid(a.sk.n_tiles, (a.n_cols + kCombCols - 1) / kCombCols);
+  combine_kernel<<<grid, 256, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+// ---- SIMT reference path ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) epilogue_kernel(EpilogueArgs a) {
+  const int i = blockIdx.x;                 // row tile
+  const int rq = threadIdx.x & 31;
+  const int j = blockIdx.y * kCombCols + (threadIdx.x >> 5);
+  if (j >= a.n_cols) return;
   const int base = a.sched.base(i);
   const int ns = a.sched.nsplit(i);
-  const int j0 = blockIdx.y * kColsPerBlock;
-
-#pragma unroll
-  for (int jj = 0; jj < kColsPerBlock; ++jj) {
-    const int j = j0 + jj;
-    if (j >= a.n_cols) return;
-    float bn = 0.0f;
-    const float *P = a.partials + ((int64_t)base * a.n_cols_pad + j) * kBlk + r;
-    for (int s = 0; s < ns; ++s) bn = __fadd_rn(bn, P[(int64_t)s * a.n_cols_pad * kBlk]);
-
-    int64_t dst;
-    float wn;
-    int b;
-    if (a.res_mode == kRes64) {
-      b = j / a.C;
-      dst = (int64_t)j * kNPix + p;
-      wn = a.z_cols[(int64_t)j * kNPix + p];
-    } else if (a.res_mode == kRes32) {
-      if (h >= 32 || w >= 32) continue;     // cropped away (:97-99)
-      b = j / a.C;
-      dst = (int64_t)j * 1024 + h * 32 + w;
-      wn = a.z_cols[(int64_t)j * kNPix + p];
-    } else {
-      const int n = j / a.C, c = j - n * a.C;
-      b = n >> 2;                           // (4B,...) re-viewed as (B,4,...): n = 4 b' + k'
-      const int k = n & 3;
-      const int r0 = (k & 1) * kTile, c0 = (k >> 1) * kTile;     // noise_padding placement
-      dst = (((int64_t)b * a.C + c) * 128 + r0 + h) * 128 + c0 + w;
-      const int f = c * kNPix + p;          // (n, pixel, channel) memory re-read as (n, channel, pixel)
-      const int cs = f % a.C, ps = f / a.C;
-      wn = a.z_cols[((int64_t)n * a.C + cs) * kNPix + ps];
-    }
-    float o = bn;
-    if (a.gamma) {
-      const float g = a.gamma[b];
-      o = __fadd_rn(__fmul_rn(bn, __fsub_rn(1.0f, g)), __fmul_rn(wn, g));
-    }
-    a.out[dst] = o;
-    if (a.out_bn) a.out_bn[dst] = bn;
-    if (a.out_wn) a.out_wn[dst] = wn;
-  }
+  const int64_t stride = (int64_t)a.n_cols_pad * kBlk;
+  const float *P = a.partials + (int64_t)base * stride + (int64_t)j * kBlk + rq * 4;
+  float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < ns; ++s) bn = add4(bn, *reinterpret_cast<const float4 *>(P + (int64_t)s * stride));
+  const OutMap m{a.z_cols, a.gamma, a.out, a.out_bn, a.out_wn, a.B, a.C, a.res_mode};
+  emit4(m, j, i * kBlk + rq * 4, bn);
 }
 
 cudaError_t launch_epilogue(const EpilogueArgs &a, cudaStream_t s) {
-  dim3 grid(a.sched.n_row_tiles, (a.n_cols + kColsPerBlock - 1) / kColsPerBlock);
-  epilogue_kernel<<<grid, 128, 0, s>>>(a);
+  dim3 grid(a.sched.n_row_tiles, (a.n_cols + kCombCols - 1) / kCombCols);
+  epilogue_kernel<<<grid, 256, 0, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -20,55 +20,88 @@ __device__ __forceinline__ float upd2(float x, float d1, float a, float d2, floa
   return __fadd_rn(__fadd_rn(x, __fmul_rn(a, d1)), __fmul_rn(g, d2));
 }
 
-// Ends a scheduled step: the last block to finish advances the step index and publishes the
-// next UNet timestep.  Safe because every block has read state[0] before it arrives here.
-__device__ __forceinline__ void finish_scheduled(int *state, float *t_next_out, int B, float t_next) {
-  __shared__ int is_last;
-  __syncthreads();
+// Scheduled steps keep their step index on the device ({step, tickets} in `state`) so that one
+// captured graph replays for every t.  Each block takes a ticket right after it has read
+// state[0]; the block that draws the last ticket knows every block has read the index and
+// advances it (and publishes the next UNet timestep) while the data path is still streaming
+// -- the atomic's latency hides behind the loads instead of extending the kernel's tail.
+__device__ __forceinline__ int read_step_and_ticket(int *state, bool &is_last) {
+  __shared__ int s_step, s_last;
   if (threadIdx.x == 0) {
+    const int step = *reinterpret_cast<volatile int *>(&state[0]);
     __threadfence();
     const int done = atomicAdd(&state[1], 1);
-    is_last = (done == (int)gridDim.x - 1);
+    s_step = step;
+    s_last = (done == (int)gridDim.x - 1);
   }
   __syncthreads();
-  if (is_last) {
-    if (t_next_out)
-      for (int b = threadIdx.x; b < B; b += blockDim.x) t_next_out[b] = t_next;
-    if (threadIdx.x == 0) {
-      state[1] = 0;
-      __threadfence();
-      state[0] = state[0] + 1;
-    }
+  is_last = s_last != 0;
+  return s_step;
+}
+__device__ __forceinline__ void advance_step(int *state, int step) {
+  if (threadIdx.x == 0) {
+    state[1] = 0;
+    __threadfence();
+    state[0] = step + 1;
   }
 }
 
+// table rows: [step][sample] x {dalpha, dgamma, t_next, 0} (per-sample, like the (B,) coefficient
+// tensors the reference forms at iadb_bn.py:311-316)
 template <bool kSched, bool kVec>
 __global__ void __launch_bounds__(256) iadb_step_kernel(IadbArgs a) {
-  float sa = 0.f, sg = 0.f, t_next = 0.f;
-  if (kSched) {
-    const int step = a.state[0];
-    const float4 row = ldg4(a.table + 4 * (int64_t)step);
-    sa = row.x; sg = row.y; t_next = row.z;
-  }
   const bool two = a.Cd == 2 * a.C;
   constexpr int V = kVec ? 4 : 1;
   const int hwv = a.HW / V;
   const int64_t total = (int64_t)a.B * a.C * hwv;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+
+  // issue the first element's loads before touching the schedule: they do not depend on it
+  float4 xv0 = make_float4(0.f, 0.f, 0.f, 0.f), u0 = xv0, v0 = xv0;
+  if (kVec && first < total) {
+    const int hw = (int)(first % hwv) * V;
+    const int64_t bc = first / hwv;
+    const int b = (int)(bc / a.C), c = (int)(bc - (int64_t)b * a.C);
+    const int64_t d1 = ((int64_t)b * a.Cd + c) * a.HW + hw;
+    xv0 = *reinterpret_cast<const float4 *>(a.x + bc * a.HW + hw);
+    u0 = ldg4(a.d + d1);
+    if (two) v0 = ldg4(a.d + d1 + (int64_t)a.C * a.HW);
+  }
+
+  const float4 *rows = nullptr;
+  int step = 0;
+  bool is_last = false;
+  if (kSched) {
+    step = read_step_and_ticket(a.state, is_last);
+    rows = reinterpret_cast<const float4 *>(a.table) + (int64_t)step * a.B;
+  }
+
+  for (int64_t idx = first; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int hw = (int)(idx % hwv) * V;
     const int64_t bc = idx / hwv;
     const int b = (int)(bc / a.C), c = (int)(bc - (int64_t)b * a.C);
-    const float da = kSched ? sa : __ldg(a.dalpha + b);
-    const float dg = kSched ? sg : (two ? __ldg(a.dgamma + b) : 0.f);
+    float da, dg;
+    if (kSched) {
+      const float4 row = __ldg(rows + b);
+      da = row.x; dg = row.y;
+    } else {
+      da = __ldg(a.dalpha + b);
+      dg = two ? __ldg(a.dgamma + b) : 0.f;
+    }
     const int64_t xo = bc * a.HW + hw;
     const int64_t d1 = ((int64_t)b * a.Cd + c) * a.HW + hw;
     const int64_t d2 = d1 + (int64_t)a.C * a.HW;
     if (kVec) {
-      const float4 xv = *reinterpret_cast<const float4 *>(a.x + xo);
-      const float4 u = ldg4(a.d + d1);
+      float4 xv, u, v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx == first) {
+        xv = xv0; u = u0; v = v0;
+      } else {
+        xv = *reinterpret_cast<const float4 *>(a.x + xo);
+        u = ldg4(a.d + d1);
+        if (two) v = ldg4(a.d + d2);
+      }
       float4 o;
       if (two) {
-        const float4 v = ldg4(a.d + d2);
         o.x = upd2(xv.x, u.x, da, v.x, dg); o.y = upd2(xv.y, u.y, da, v.y, dg);
         o.z = upd2(xv.z, u.z, da, v.z, dg); o.w = upd2(xv.w, u.w, da, v.w, dg);
       } else {
@@ -81,7 +114,11 @@ __global__ void __launch_bounds__(256) iadb_step_kernel(IadbArgs a) {
       a.x_out[xo] = two ? upd2(xv, a.d[d1], da, a.d[d2], dg) : upd1(xv, a.d[d1], da);
     }
   }
-  if (kSched) finish_scheduled(a.state, a.t_next_out, a.B, t_next);
+  if (kSched && is_last) {
+    if (a.t_next_out)
+      for (int b = threadIdx.x; b < a.B; b += blockDim.x) a.t_next_out[b] = __ldg(rows + b).z;
+    advance_step(a.state, step);
+  }
 }
 
 static int grid_for(int64_t work_items, int threads) {
@@ -119,7 +156,9 @@ __device__ __forceinline__ float ddim1(float x, float e, float z, bool has_noise
 
 template <bool kVec>
 __global__ void __launch_bounds__(256) ddim_step_kernel(DdimArgs a) {
-  const int step = a.state ? a.state[0] : 0;
+  int step = 0;
+  bool is_last = false;
+  if (a.state) step = read_step_and_ticket(a.state, is_last);
   const float *row = a.coef + 8 * (int64_t)step;
   const float c[5] = {__ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), __ldg(row + 4)};
   const float t_next = __ldg(row + 5);
@@ -140,7 +179,11 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(DdimArgs a) {
       a.x_out[idx] = ddim1(a.x[idx], a.eps[idx], hn ? a.noise[idx] : 0.f, hn, a.clip, c);
     }
   }
-  if (a.state) finish_scheduled(a.state, a.t_next_out, a.B, t_next);
+  if (a.state && is_last) {
+    if (a.t_next_out)
+      for (int b = threadIdx.x; b < a.B; b += blockDim.x) a.t_next_out[b] = t_next;
+    advance_step(a.state, step);
+  }
 }
 
 cudaError_t launch_ddim_step(const DdimArgs &a, cudaStream_t s) {

@@ -52,6 +52,8 @@ class IadbStepper:
 
     def __init__(self, table_cpu: torch.Tensor, first_t: float, batch: int, device):
         self.device = torch.device(device)
+        if table_cpu.dim() != 3 or table_cpu.shape[1] != batch or table_cpu.shape[2] != 4:
+            raise ValueError(f"schedule table must be (T, {batch}, 4), got {tuple(table_cpu.shape)}")
         self.n_steps = table_cpu.shape[0]
         self.table = table_cpu.to(self.device).contiguous()
         self.state = torch.zeros(2, dtype=torch.int32, device=self.device)       # {step index, blocks done}
@@ -158,11 +160,11 @@ class IadbSampler:
         if table is None:
             _expected_out_channels(noise_type, out_channel, C)
             table, first_t = iadb_table(nb_step, scheduler_alpha, scheduler_gamma,
-                                        tuple(float(p) for p in scheduler_params), alpha_param)
+                                        tuple(float(p) for p in scheduler_params), alpha_param, batch=B)
         else:
             table = table.clone()
         if not (noise_type in TWO_HEAD and out_channel == 2 * C):
-            table[:, 1] = 0.0
+            table[..., 1] = 0.0
         self.stepper = IadbStepper(table, first_t, B, self.device)
         self.x = torch.zeros(self.shape, dtype=torch.float32, device=self.device)
         call = _call_model_iadb(model)
@@ -335,7 +337,7 @@ def sample_latent_iadb(model, noise, num_steps, noise_type="gaussianBN", out_cha
             raise NotImplementedError
     elif noise_type != "gaussian":
         raise NotImplementedError
-    table, first_t = latent_table(num_steps)
+    table, first_t = latent_table(num_steps, batch=x.shape[0])
     sampler = IadbSampler(model, x.shape, num_steps, out_channel=out_channels, noise_type=noise_type, device=x.device,
                           graph="step" if use_graph else None, table=table, first_t=first_t)
     return sampler(x)

@@ -55,26 +55,37 @@ def get_scheduler_gamma(x, scheduler, scheduler_params, nb_steps):
 
 
 def iadb_table(nb_step, scheduler_alpha="linear", scheduler_gamma="sigmoid", scheduler_params=(1000.0, 0.0, 3.0),
-               alpha_param=1000.0):
-    """(T,4) fp32 CPU table, row r <-> loop step t = T-1-r (iadb_bn.py:304-316):
+               alpha_param=1000.0, batch=1):
+    """(T,B,4) fp32 CPU table; row [r, b] <-> loop step t = T-1-r, sample b (iadb_bn.py:304-316):
     {alpha(t+1)-alpha(t), gamma(t+1)-gamma(t), alpha(t) [= the NEXT step's UNet timestep], 0}
-    and the first UNet timestep alpha(T)."""
-    t = torch.arange(nb_step - 1, -1, -1, dtype=torch.int64)          # tt for each row
-    a_start = get_scheduler((t + 1).float(), scheduler_alpha, nb_step, alpha_param)
-    a_end = get_scheduler(t.float(), scheduler_alpha, nb_step, alpha_param)
-    g_start = get_scheduler_gamma((t + 1).float(), scheduler_gamma, scheduler_params, nb_step)
-    g_end = get_scheduler_gamma(t.float(), scheduler_gamma, scheduler_params, nb_step)
-    table = torch.stack([a_start - a_end, g_start - g_end, a_end, torch.zeros_like(a_end)], dim=1).contiguous()
-    return table.float(), float(a_start[0])
+    and the first UNet timestep alpha(T).
+
+    Every step is evaluated on a (B,)-shaped int64 -> float tensor exactly like the reference
+    (``tt = torch.randint(t, t + 1, (B,))``): torch's CPU kernels send short tensors and loop
+    tails through scalar libm and full vectors through SLEEF, which differ in the last ulp, so
+    the coefficient a sample gets depends on B and on its position in the batch.  Evaluating the
+    whole schedule as one (T,) tensor would be faster and is NOT bit-identical."""
+    rows = []
+    for t in reversed(range(nb_step)):
+        tt = torch.full((batch,), t, dtype=torch.int64)
+        a_start = get_scheduler((tt + 1).float(), scheduler_alpha, nb_step, alpha_param)
+        a_end = get_scheduler(tt.float(), scheduler_alpha, nb_step, alpha_param)
+        g_start = get_scheduler_gamma((tt + 1).float(), scheduler_gamma, scheduler_params, nb_step)
+        g_end = get_scheduler_gamma(tt.float(), scheduler_gamma, scheduler_params, nb_step)
+        if not rows:
+            first_t = float(a_start[0])
+        rows.append(torch.stack([a_start - a_end, g_start - g_end, a_end, torch.zeros_like(a_end)], dim=1))
+    return torch.stack(rows).float().contiguous(), first_t
 
 
-def latent_table(num_inference_steps):
+def latent_table(num_inference_steps, batch=1):
     """IADBScheduler.step coefficients (latent_iadb_bn_diffusers.py:99-103): python floats
     (t+1)/N - t/N for alpha and gamma alike, cast to fp32 when torch multiplies the tensor;
-    UNet timestep alpha = (t+1)/N (:525)."""
+    UNet timestep alpha = (t+1)/N (:525).  Shape (N,B,4), identical across the batch."""
     N = num_inference_steps
     rows = []
     for t in reversed(range(N)):
         d = (t + 1) / N - t / N
         rows.append([d, d, t / N, 0.0])
-    return torch.tensor(rows, dtype=torch.float64).float().contiguous(), float(torch.tensor(1.0 * N / N))
+    table = torch.tensor(rows, dtype=torch.float64).float()
+    return table[:, None, :].expand(N, batch, 4).contiguous(), float(torch.tensor(1.0 * N / N))

@@ -105,10 +105,12 @@ int bndm_iadb_step_f32(float *x_out, const float *x, const float *d, const float
                        const float *dgamma, int B, int C, int HW, int d_channels, void *stream);
 
 /* Same update driven by a device-resident schedule so that ONE captured CUDA graph of
- * [UNet, step] replays for every t:  row = table[*step_idx]  = {dalpha, dgamma, t_next, 0};
- * after the update the kernel fills t_next_out[0..B) with row.t_next (the next UNet
- * "timestep" = alpha_start of the following step, iadb_bn.py:311,319) and increments
- * *step_idx.  `state` is 2 ints on the device: {step_idx, blocks_done}.                    */
+ * [UNet, step] replays for every t.  `table` is [T][B] rows of 4 floats
+ * {dalpha, dgamma, t_next, 0}: per step AND per sample, like the (B,) coefficient tensors the
+ * reference forms each step (iadb_bn.py:306-316).  Row used for sample b: table[*step_idx][b].
+ * The kernel also fills t_next_out[b] with its row's t_next (the next UNet "timestep" =
+ * alpha_start of the following step, iadb_bn.py:311,319) and increments *step_idx.
+ * `state` is 2 ints on the device: {step_idx, tickets}, both 0 before the first step.      */
 int bndm_iadb_step_sched_f32(float *x_out, const float *x, const float *d, const float *table,
                              int *state, float *t_next_out, int B, int C, int HW, int d_channels,
                              void *stream);
@@ -123,6 +125,11 @@ int bndm_iadb_step_sched_f32(float *x_out, const float *x, const float *d, const
 int bndm_ddim_step_f32(float *x_out, const float *x, const float *eps, const float *noise,
                        const float *coef, int *state, float *t_next_out, int B, int clip, int64_t n,
                        void *stream);
+
+/* Host-only consistency check of the contraction kernel's stream-K work split (no device
+ * work; used by the CPU test-suite).  0 if every pipeline stage is covered exactly once and
+ * the combine kernel's view of the partial tiles matches what the GEMM kernel writes.       */
+int bndm_debug_streamk_check(int n_tiles, int dense, int n_colblk, int num_sms);
 
 /* Image post-processing of the test drivers (iadb_bn.py:796-816, ddim_diffusers.py:687-688):
  * out_u8[b,h,w,c] = round(clamp(x[b,c,h,w]/2 + 0.5, 0, 1) * 255), NCHW fp32 -> NHWC uint8. */
