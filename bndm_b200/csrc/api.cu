@@ -44,8 +44,8 @@ using namespace bndm;
 
 struct bndm_L {
   const float *L = nullptr;     // caller's matrix (bound, not owned)
-  float *L_hi = nullptr;        // owned: tf32 hi / lo copies for the tcgen05 path
-  float *L_lo = nullptr;
+  float *Lt = nullptr;          // owned: tcgen05 operand, tf32 hi|lo stage blocks (triangular set if L is lower-triangular)
+  float *Lt_dense = nullptr;    // owned: all 4096 stage blocks of a triangular L, built on the first BNDM_FORCE_DENSE call
   int n = 0;
   int lower_triangular = 0;
   int sm100 = 0;
@@ -53,7 +53,7 @@ struct bndm_L {
   int cap_cols = 0;
   int req_cols = 0;             // max_columns the workspace was sized for
   size_t cap_partial = 0;
-  float *z_raw = nullptr, *z_hi = nullptr, *z_lo = nullptr, *partials = nullptr;
+  float *z_raw = nullptr, *zt = nullptr, *partials = nullptr;
   int64_t ws_bytes = 0;
   // optional per-launch timing (bndm_profile_enable)
   int profile = 0;
@@ -102,10 +102,9 @@ static size_t partial_elems(int n_cols) {
 
 static void free_ws(bndm_L *h) {
   cudaFree(h->z_raw);
-  cudaFree(h->z_hi);
-  cudaFree(h->z_lo);
+  cudaFree(h->zt);
   cudaFree(h->partials);
-  h->z_raw = h->z_hi = h->z_lo = h->partials = nullptr;
+  h->z_raw = h->zt = h->partials = nullptr;
   h->cap_cols = 0;
   h->req_cols = 0;
   h->cap_partial = 0;
@@ -128,8 +127,7 @@ static int alloc_ws(bndm_L *h, int max_columns) {
   }
   const size_t zb = (size_t)cols_pad * kNPix * sizeof(float);
   CK(cudaMalloc(&h->z_raw, zb));
-  CK(cudaMalloc(&h->z_hi, zb));
-  CK(cudaMalloc(&h->z_lo, zb));
+  CK(cudaMalloc(&h->zt, 2 * zb));
   CK(cudaMalloc(&h->partials, pe * sizeof(float)));
   h->cap_cols = cols_pad;
   h->req_cols = max_columns;
@@ -173,12 +171,11 @@ int bndm_prepare_L(const float *L_dev, int n, int max_columns, void *stream, bnd
   h->lower_triangular = host_flag ? 0 : 1;
 
   if (h->sm100) {
-    const size_t lb = (size_t)n * n * sizeof(float);
-    e = cudaMalloc(&h->L_hi, lb);
-    if (e == cudaSuccess) e = cudaMalloc(&h->L_lo, lb);
-    if (e == cudaSuccess) e = launch_split_tf32(L_dev, h->L_hi, h->L_lo, (int64_t)n * n, s);
+    const int dense = h->lower_triangular ? 0 : 1;
+    e = cudaMalloc(&h->Lt, tile_L_blocks(dense) * kLBlockFloats * sizeof(float));
+    if (e == cudaSuccess) e = launch_tile_L(L_dev, h->Lt, dense, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { bndm_free_L(h); return fail_cuda(e, "tf32 split of L"); }
+    if (e != cudaSuccess) { bndm_free_L(h); return fail_cuda(e, "tf32 split / tiling of L"); }
   }
   int rc = alloc_ws(h, max_columns);
   if (rc != BNDM_OK) { bndm_free_L(h); return rc; }
@@ -223,8 +220,8 @@ int bndm_free_L(bndm_L *h) {
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   free_ws(h);
-  cudaFree(h->L_hi);
-  cudaFree(h->L_lo);
+  cudaFree(h->Lt);
+  cudaFree(h->Lt_dense);
   delete h;
   return BNDM_OK;
 }
@@ -267,8 +264,8 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
   PackArgs p;
   p.src = z;
   p.z_raw = need_raw ? h->z_raw : nullptr;
-  p.z_hi = simt ? nullptr : h->z_hi;
-  p.z_lo = simt ? nullptr : h->z_lo;
+  p.zt = simt ? nullptr : h->zt;
+  p.nb = nb;
   p.n_cols = n_cols;
   p.n_cols_pad = n_cols_pad;
   p.B = B;
@@ -308,10 +305,17 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
   } else {
     // K1b (tcgen05, persistent stream-K) -> K1c (ordered combine + lerp + layout)
     TcGemmArgs g;
-    g.L_hi = h->L_hi;
-    g.L_lo = h->L_lo;
-    g.z_hi = h->z_hi;
-    g.z_lo = h->z_lo;
+    g.Lt = h->Lt;
+    if (dense && h->lower_triangular) {
+      // BNDM_FORCE_DENSE on a triangular L (testing): needs the full block set, built once
+      if (!h->Lt_dense) {
+        if (stream_is_capturing(s)) { set_error("dense operand copy requested during stream capture"); return BNDM_ERR_WORKSPACE; }
+        CK(cudaMalloc(&h->Lt_dense, tile_L_blocks(1) * kLBlockFloats * sizeof(float)));
+        CK(launch_tile_L(h->L, h->Lt_dense, 1, s));
+      }
+      g.Lt = h->Lt_dense;
+    }
+    g.zt = h->zt;
     g.partials = h->partials;
     g.n_cols_pad = n_cols_pad;
     g.nb = nb;

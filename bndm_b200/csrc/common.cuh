@@ -47,8 +47,9 @@ struct Schedule {
 struct PackArgs {
   const float *src;   // white source
   float *z_raw;       // [n_cols_pad][4096] packed raw columns (may be null if src is already packed)
-  float *z_hi;        // [n_cols_pad][4096] tf32 hi part (null for SIMT path)
-  float *z_lo;        // [n_cols_pad][4096] tf32 lo part
+  float *zt;          // tcgen05 operand: stage blocks [col block][128 stages][zh rows | zl rows][32 k],
+                      // SWIZZLE_128B image (null for the SIMT path); see noise_gemm_tc.cu
+  int nb;             // columns per column block of zt
   int n_cols;         // B*C*(tiles per image)
   int n_cols_pad;     // rows of the packed buffers (zero-filled above n_cols)
   int B, C;
@@ -79,7 +80,16 @@ struct EpilogueArgs {
 cudaError_t launch_epilogue(const EpilogueArgs &a, cudaStream_t s);
 
 cudaError_t launch_white128(const float *x, float *out, int B, int C, cudaStream_t s);
-cudaError_t launch_split_tf32(const float *src, float *hi, float *lo, int64_t n, cudaStream_t s);
+// L -> stage blocks [Lh tile | Ll tile] in the SWIZZLE_128B shared-memory image (noise_gemm_tc.cu);
+// n_blocks = 2112 (lower-triangular, blocks of row tile i start at 2 i (i + 1)) or 4096 (dense)
+cudaError_t launch_tile_L(const float *L, float *Lt, int dense, cudaStream_t s);
+inline size_t tile_L_blocks(int dense) { return dense ? (size_t)kNumBlk * (kNPix / kStageK) : (size_t)2 * kNumBlk * (kNumBlk + 1); }
+constexpr size_t kLBlockFloats = 2 * kBlk * kStageK;   // 32 KiB per stage block
+
+// byte offset of element (row r, k-in-stage kk) inside a K-major SWIZZLE_128B tile of 128-byte rows
+__host__ __device__ inline uint32_t sw128_offset(int r, int kk) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((kk >> 2) ^ (r & 7)) & 7) << 4) + (kk & 3) * 4);
+}
 cudaError_t launch_tri_check(const float *L, int n, int *flag_dev, cudaStream_t s);
 
 // ---- stream-K schedule of the tensor-core contraction (see noise_gemm_tc.cu) ---------------
@@ -123,11 +133,11 @@ inline StreamK make_streamk(int n_tiles, int dense, int n_colblk, int num_sms) {
 }
 
 struct TcGemmArgs {
-  const float *L_hi, *L_lo;   // [4096][4096] tf32-split copies of L
-  const float *z_hi, *z_lo;   // [n_cols_pad][4096]
+  const float *Lt;            // stage blocks of L (launch_tile_L), triangular or dense per sk.dense
+  const float *zt;            // stage blocks of z (launch_pack)
   float *partials;            // [n_slots][nb][128]
   int n_cols_pad;             // n_colblk * nb
-  int nb;                     // columns per column block (multiple of 16, <= 256)
+  int nb;                     // columns per column block (multiple of 16, <= 128)
   StreamK sk;
 };
 cudaError_t launch_gemm_tc(const TcGemmArgs &a, cudaStream_t s);

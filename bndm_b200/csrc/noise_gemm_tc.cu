@@ -1,44 +1,53 @@
 // K1b (tensor-core variant): the triangular contraction  bn[j][p] = sum_k L[p][k] * z[j][k]
-// on tcgen05 with TMA-staged operands and TMEM accumulators.  sm_100a only.
+// on tcgen05 with bulk-copy (TMA) staged operands and TMEM accumulators.  sm_100a only.
 //
-// PERSISTENT, STREAM-K.  The work is the list of "k-stages" (one 128-row tile of L x 32 k
-// values x one column block) of every row tile, triangular rows first to last:
-//     row tile i needs k < 128 (i + 1)  =>  4 (i + 1) stages   (lower-triangular L)
-//                                          128 stages           (dense L)
-// The W stages are cut into G = min(#SMs, W) equal contiguous ranges, one per CTA, so every
-// SM streams the same number of L bytes and issues the same number of MMAs (+-1 stage),
-// whatever the triangle looks like.  A CTA's range crosses row-tile borders; each maximal
-// piece inside one row tile is a SEGMENT that accumulates in its own TMEM buffer and is
-// written out as one partial tile  P[slot][column][128 rows], slot = cta + tile index
-// (strictly increasing along the global order, hence unique).  The combine kernel
-// (noise_epilogue.cu) adds the partials of a row tile in ascending k order in fp32 --
-// deterministic, no atomics.
+// OPERAND LAYOUT (built once per L by tile_L_kernel, per call for z by pack_kernel; see
+// noise_pack.cu).  A "stage" is one 128-row tile of L x 32 k values.  Both operands live in
+// global memory as a sequence of stage blocks that already have the shared-memory image the
+// tensor core wants (K-major, 128-byte rows, SWIZZLE_128B: 16-byte chunk c of row r sits at
+// chunk c ^ (r & 7) of its 8-row / 1024-byte group), so ONE linear cp.async.bulk per operand
+// per stage brings a block in -- no tensor maps, every DRAM burst a full 32 KiB / 2 nb * 128 B:
+//     L block (tile i, stage s)  = [ Lh tile 16 KiB | Ll tile 16 KiB ]          at Lt + 32 KiB * (cum(i) + s)
+//     z block (col block cb, s)  = [ zh rows 0..nb-1 | zl rows nb..2nb-1 ]      at zt + 256 nb B * (128 cb + s)
+// Only the blocks a lower-triangular L needs exist: row tile i has 4 (i + 1) of them.
 //
-// fp32-grade accuracy from TF32 tensor cores by error compensation (3xTF32):
-//   L = Lh + Ll, z = zh + zl (each part exactly representable in tf32, hi rounded rna)
-//   L*z ~= Ll*zh + Lh*zl + Lh*zh          (the dropped Ll*zl term is ~2^-22 relative)
+// fp32-GRADE ACCURACY FROM TF32 TENSOR CORES.  L = Lh + Ll, z = zh + zl (each part exactly
+// representable in tf32, hi rounded rna), and  L z ~= Lh zh + (Lh zl + Ll zh); the dropped
+// Ll zl term is ~2^-22 relative.  Per 8 k values the issuer sends TWO MMAs:
+//     D[:, 0:2nb]  += Lh x [zh | zl]      (N = 2 nb: main product and first correction side by side)
+//     D[:, nb:2nb] += Ll x  zh            (N = nb:   second correction)
+// so Lh is read from shared memory once instead of twice, and the large main sums never share an
+// accumulator with the small corrections.  The tensor core ADDS INTO TMEM WITH TRUNCATION (measured:
+// error grows with the length of the in-TMEM chain and is biased towards zero), so a chain is
+// cut after `chain` stages (4 => 16 adds): the epilogue warps pull the two accumulator halves
+// out of TMEM, add them in fp32 round-to-nearest into per-thread running sums, and the issuer
+// carries on in the other TMEM buffer meanwhile.
 //
-// CTA = 6 warps: warp 0 = TMA producer (1 lane), warp 1 = TMEM alloc + MMA issuer (1 lane),
-// warps 2..5 = epilogue (TMEM -> registers -> partial tile).  Three pipelines: the smem
-// stage ring (TMA <-> MMA), two TMEM accumulator buffers (MMA <-> epilogue, so a segment's
-// drain overlaps the next segment's MMAs), and the static stream-K schedule.
-// Operand tiles are [rows][32 fp32] = 128-byte rows in the canonical K-major SWIZZLE_128B
-// layout that both TMA (CU_TENSOR_MAP_SWIZZLE_128B) and the UMMA smem descriptor expect.
-#include <cuda.h>
+// PERSISTENT, STREAM-K.  The W = (column blocks) x (stages) units are cut into G = min(#SMs, W)
+// equal contiguous ranges, one per CTA, so every SM streams the same number of L bytes and
+// issues the same number of MMAs (+-1 stage) whatever the triangle looks like.  A CTA's range
+// crosses row-tile borders; each maximal piece inside one row tile is a SEGMENT written out as
+// one partial tile P[slot][column][128 rows], slot = cta + tile index (unique).  The combine
+// kernel (noise_epilogue.cu) adds the partials of a row tile in ascending k order in fp32 --
+// deterministic, no atomics on data.
+//
+// CTA = 6 warps: warp 0 = producer (1 lane issues the bulk copies), warp 1 = TMEM alloc + MMA
+// issuer (1 lane), warps 2..5 = epilogue.  Pipelines: smem stage ring (producer <-> issuer),
+// two TMEM accumulator buffers (issuer <-> epilogue), the static stream-K schedule.
 #include <stdlib.h>
 
 #include "common.cuh"
 
 namespace bndm {
 
-constexpr int kATileBytes = kBlk * kStageK * 4;   // 16 KiB
 constexpr int kUmmaK = 8;                         // tf32: 32 bytes of K per tcgen05.mma
 constexpr int kThreads = 192;
 constexpr uint32_t kSpinLimit = 1u << 27;         // bounded spins: a protocol bug traps instead of hanging the GPU
 
-// L2 eviction-priority policies for TMA loads (createpolicy encodings)
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;   // L: streamed once per column block
-constexpr uint64_t kEvictLast = 0x14F0000000000000ull;    // z: re-read by every row tile
+// L2 eviction-priority policies for bulk loads (createpolicy encodings)
+constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
 // ---------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -71,16 +80,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1,
-                                            uint64_t policy) {
+// linear global -> shared bulk copy (TMA engine), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
@@ -106,18 +111,7 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (lane = thread)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t *r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread (lane = thread)
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -139,28 +133,63 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major A/B,
+// N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlk >> 4) << 24);
+}
 
 // ------------------------------------------------------------------------------- kernel
 struct TcKernelArgs {
-  float *partials;
-  int nb;             // columns per column block = UMMA N
+  const float *Lt;    // stage blocks of L (hi | lo)
+  const float *zt;    // stage blocks of z (hi rows | lo rows)
+  float *partials;    // [n_slots][NB][128]
   int stages;         // smem ring depth
-  uint32_t tmem_cols; // 2 accumulator buffers of buf_cols columns (power of two)
-  uint32_t buf_cols;  // power of two >= max(32, nb)
-  uint32_t idesc;
+  int chain;          // stages per TMEM accumulation chain
+  uint64_t policy_L;
   StreamK sk;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_Lh, const __grid_constant__ CUtensorMap map_Ll,
-               const __grid_constant__ CUtensorMap map_zh, const __grid_constant__ CUtensorMap map_zl,
-               const TcKernelArgs a) {
+// One (<= chain)-stage piece of a segment; every role walks the same sequence.
+struct ChainWalk {
+  const StreamK sk;
+  const int g_end, chain;
+  int g;
+  int cb, tile, s0, n;      // current chain: stages [s0, s0 + n) of row tile `tile`, column block cb
+  bool first, last;         // first / last chain of its segment
+  int seg_end;
+  __device__ ChainWalk(const StreamK &k, int cta, int chain_) : sk(k), g_end(k.cta_begin(cta + 1)), chain(chain_) {
+    g = k.cta_begin(cta);
+    seg_end = g;
+  }
+  __device__ bool next() {
+    if (g >= g_end) return false;
+    first = (g == seg_end);
+    if (first) {
+      sk.decode(g, cb, tile, s0);
+      seg_end = min(g_end, sk.tile_end(cb, tile));
+    } else {
+      s0 += n;
+    }
+    n = min(chain, seg_end - g);
+    g += n;
+    last = (g == seg_end);
+    return true;
+  }
+};
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcKernelArgs a) {
+  constexpr uint32_t kLBlockBytes = 2 * kBlk * kStageK * 4;       // 32 KiB: Lh tile | Ll tile
+  constexpr uint32_t kZBlockBytes = 2 * NB * kStageK * 4;         // zh rows | zl rows
+  constexpr uint32_t kStageBytes = kLBlockBytes + kZBlockBytes;
+  constexpr uint32_t kBufCols = 2 * NB;                           // main | correction
+  constexpr uint32_t kTmemCols = 4 * NB <= 32 ? 32 : 4 * NB <= 64 ? 64 : 4 * NB <= 128 ? 128 : 4 * NB <= 256 ? 256 : 512;
+  static_assert(NB % 16 == 0 && NB >= 16 && NB <= 128, "column block must be a multiple of 16 in [16, 128]");
+
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages] x {A_hi, A_lo, B_hi, B_lo}, then barriers
-  const uint32_t b_tile_bytes = (uint32_t)a.nb * kStageK * 4;
-  const uint32_t stage_bytes = 2 * kATileBytes + 2 * b_tile_bytes;
   uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(base + (size_t)a.stages * stage_bytes);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(base + (size_t)a.stages * kStageBytes);
   uint64_t *empty_bar = full_bar + a.stages;
   uint64_t *acc_full = empty_bar + a.stages;      // [2]
   uint64_t *acc_empty = acc_full + 2;             // [2]
@@ -168,15 +197,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_Lh, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const StreamK sk = a.sk;
   const int cta = blockIdx.x;
-  const int g_begin = sk.cta_begin(cta), g_end = sk.cta_begin(cta + 1);
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&map_Lh);
-    prefetch_tmap(&map_Ll);
-    prefetch_tmap(&map_zh);
-    prefetch_tmap(&map_zl);
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -187,104 +210,95 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_Lh, const __grid_constant
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, a.tmem_cols);
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= producer: one bulk copy per operand per stage =================
     if (lane == 0) {
+      ChainWalk w(a.sk, cta, a.chain);
       int it = 0;
-      for (int g = g_begin; g < g_end;) {
-        int cb, tile, s0;
-        sk.decode(g, cb, tile, s0);
-        const int seg_end = min(g_end, sk.tile_end(cb, tile));
-        const int row0 = tile * kBlk, col0 = cb * a.nb;
-        for (int s = s0; s < s0 + (seg_end - g); ++s, ++it) {
+      while (w.next()) {
+        const float *Lblk = a.Lt + (size_t)(a.sk.cum(w.tile) + w.s0) * (kLBlockBytes / 4);
+        const float *zblk = a.zt + (size_t)(w.cb * (kNPix / kStageK) + w.s0) * (kZBlockBytes / 4);
+        for (int n = 0; n < w.n; ++n, ++it) {
           const int st = it % a.stages;
           const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
           mbar_wait(&empty_bar[st], ph ^ 1u);
-          const uint32_t sa = smem_u32(base + (size_t)st * stage_bytes);
-          const int k0 = s * kStageK;
-          mbar_expect_tx(&full_bar[st], stage_bytes);
-          tma_load_2d(sa, &map_Lh, &full_bar[st], k0, row0, kEvictFirst);
-          tma_load_2d(sa + kATileBytes, &map_Ll, &full_bar[st], k0, row0, kEvictFirst);
-          tma_load_2d(sa + 2 * kATileBytes, &map_zh, &full_bar[st], k0, col0, kEvictLast);
-          tma_load_2d(sa + 2 * kATileBytes + b_tile_bytes, &map_zl, &full_bar[st], k0, col0, kEvictLast);
+          const uint32_t sa = smem_u32(base + (size_t)st * kStageBytes);
+          mbar_expect_tx(&full_bar[st], kStageBytes);
+          bulk_load(sa, Lblk + (size_t)n * (kLBlockBytes / 4), kLBlockBytes, &full_bar[st], a.policy_L);
+          bulk_load(sa + kLBlockBytes, zblk + (size_t)n * (kZBlockBytes / 4), kZBlockBytes, &full_bar[st], kEvictLast);
         }
-        g = seg_end;
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      int it = 0, seg = 0;
-      for (int g = g_begin; g < g_end; ++seg) {
-        int cb, tile, s0;
-        sk.decode(g, cb, tile, s0);
-        const int seg_end = min(g_end, sk.tile_end(cb, tile));
-        const int buf = seg & 1;
-        mbar_wait(&acc_empty[buf], (((uint32_t)seg >> 1) & 1u) ^ 1u);     // epilogue drained this buffer
+      constexpr uint32_t idesc_wide = umma_idesc(2 * NB), idesc_narrow = umma_idesc(NB);
+      ChainWalk w(a.sk, cta, a.chain);
+      int it = 0, ch = 0;
+      for (; w.next(); ++ch) {
+        const int buf = ch & 1;
+        mbar_wait(&acc_empty[buf], (((uint32_t)ch >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)buf * a.buf_cols;
-        for (int n = 0; n < seg_end - g; ++n, ++it) {
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * kBufCols;
+        for (int n = 0; n < w.n; ++n, ++it) {
           const int st = it % a.stages;
           const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
           mbar_wait(&full_bar[st], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(base + (size_t)st * stage_bytes);
+          const uint32_t sa = smem_u32(base + (size_t)st * kStageBytes);
           const uint64_t dAh = umma_desc(sa);
-          const uint64_t dAl = umma_desc(sa + kATileBytes);
-          const uint64_t dBh = umma_desc(sa + 2 * kATileBytes);
-          const uint64_t dBl = umma_desc(sa + 2 * kATileBytes + b_tile_bytes);
+          const uint64_t dAl = umma_desc(sa + kLBlockBytes / 2);
+          const uint64_t dB = umma_desc(sa + kLBlockBytes);
 #pragma unroll
           for (int kk = 0; kk < kStageK / kUmmaK; ++kk) {
             const uint64_t adv = (uint64_t)((kk * kUmmaK * 4) >> 4);   // +32 B inside the swizzle row
-            umma_tf32(tmem_d, dAl + adv, dBh + adv, a.idesc, (n | kk) != 0);
-            umma_tf32(tmem_d, dAh + adv, dBl + adv, a.idesc, 1u);
-            umma_tf32(tmem_d, dAh + adv, dBh + adv, a.idesc, 1u);
+            umma_tf32(tmem_d, dAh + adv, dB + adv, idesc_wide, (n | kk) != 0);      // Lh x [zh | zl]
+            umma_tf32(tmem_d + NB, dAl + adv, dB + adv, idesc_narrow, 1u);          // Ll x zh
           }
           umma_commit(&empty_bar[st]);       // frees the smem stage when these MMAs retire
         }
-        umma_commit(&acc_full[buf]);         // this segment's accumulator is complete
-        g = seg_end;
+        umma_commit(&acc_full[buf]);         // this chain's accumulators are complete
       }
     }
   } else {
-    // ================= epilogue: TMEM -> partial tile =================
+    // ================= epilogue: TMEM -> fp32 running sums -> partial tile =================
     const int q = warp & 3;               // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;          // row inside the tile
-    int seg = 0;
-    for (int g = g_begin; g < g_end; ++seg) {
-      int cb, tile, s0;
-      sk.decode(g, cb, tile, s0);
-      const int seg_end = min(g_end, sk.tile_end(cb, tile));
-      const int buf = seg & 1;
-      mbar_wait(&acc_full[buf], ((uint32_t)seg >> 1) & 1u);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * a.buf_cols;
-      float *P = a.partials + ((int64_t)sk.slot(cta, cb, tile) * a.nb) * kBlk + r;
-      int c = 0;
-      for (; c + 32 <= a.nb; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c, v);
-        tmem_ld_wait();
+    float acc[NB];
+    ChainWalk w(a.sk, cta, a.chain);
+    for (int ch = 0; w.next(); ++ch) {
+      const int buf = ch & 1;
+      if (w.first) {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) P[(int64_t)(c + e) * kBlk] = __uint_as_float(v[e]);   // 32 lanes -> 128 B rows
+        for (int c = 0; c < NB; ++c) acc[c] = 0.0f;
       }
-      if (c < a.nb) {                     // nb is a multiple of 16
-        uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c, v);
+      mbar_wait(&acc_full[buf], ((uint32_t)ch >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kBufCols;
+#pragma unroll
+      for (int c = 0; c < NB; c += 16) {
+        uint32_t m[16], x[16];
+        tmem_ld16(taddr + (uint32_t)c, m);
+        tmem_ld16(taddr + (uint32_t)(NB + c), x);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) P[(int64_t)(c + e) * kBlk] = __uint_as_float(v[e]);
+        for (int e = 0; e < 16; ++e)
+          acc[c + e] = __fadd_rn(acc[c + e], __fadd_rn(__uint_as_float(m[e]), __uint_as_float(x[e])));
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-      g = seg_end;
+      if (w.last) {
+        float *P = a.partials + ((int64_t)a.sk.slot(cta, w.cb, w.tile) * NB) * kBlk + r;
+#pragma unroll
+        for (int c = 0; c < NB; ++c) P[(int64_t)c * kBlk] = acc[c];          // 32 lanes -> 128 B rows
+      }
     }
   }
 
@@ -292,47 +306,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_Lh, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, a.tmem_cols);
+    tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
 // --------------------------------------------------------------------------------- host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn) return fn;
-  void *p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
-    return nullptr;
-  fn = reinterpret_cast<EncodeTiledFn>(p);
-  return fn;
-}
-
-// 2-D fp32 row-major [rows][4096] tensor, box = [box_rows][32], 128-byte swizzle
-static bool make_map(CUtensorMap *m, const float *ptr, int rows, int box_rows) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return false;
-  cuuint64_t dims[2] = {(cuuint64_t)kNPix, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)kNPix * 4};
-  cuuint32_t box[2] = {(cuuint32_t)kStageK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
 int tc_max_nb() {
   static int v = 0;
   if (!v) {
-    v = 256;
+    v = 128;
     if (const char *e = getenv("BNDM_TC_MAX_NB")) {
       const int x = atoi(e);
-      if (x >= 16 && x <= 256) v = x / 16 * 16;
+      if (x >= 16 && x <= 128) v = x / 16 * 16;
     }
   }
   return v;
@@ -358,35 +343,54 @@ int tc_num_sms() {
   return n;
 }
 
-cudaError_t launch_gemm_tc(const TcGemmArgs &g, cudaStream_t s) {
-  CUtensorMap mLh, mLl, mzh, mzl;
-  if (!make_map(&mLh, g.L_hi, kNPix, kBlk) || !make_map(&mLl, g.L_lo, kNPix, kBlk) ||
-      !make_map(&mzh, g.z_hi, g.n_cols_pad, g.nb) || !make_map(&mzl, g.z_lo, g.n_cols_pad, g.nb)) {
-    set_error("cuTensorMapEncodeTiled failed (nb=%d, cols=%d)", g.nb, g.n_cols_pad);
-    return cudaErrorInvalidValue;
+static int tc_chain() {
+  static int v = 0;
+  if (!v) {
+    v = 4;
+    if (const char *e = getenv("BNDM_TC_CHAIN")) {
+      const int x = atoi(e);
+      if (x >= 1 && x <= 4096) v = x;
+    }
   }
-  TcKernelArgs a;
-  a.partials = g.partials;
-  a.nb = g.nb;
-  a.sk = g.sk;
-  const uint32_t stage_bytes = 2 * kATileBytes + 2 * (uint32_t)g.nb * kStageK * 4;
-  int stages = (int)((224u * 1024u) / stage_bytes);
-  if (stages > 8) stages = 8;
-  if (stages < 2) stages = 2;
-  a.stages = stages;
-  uint32_t cols = 32;
-  while (cols < (uint32_t)g.nb) cols <<= 1;
-  a.buf_cols = cols;
-  a.tmem_cols = 2 * cols;
-  // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major A/B,
-  // N>>3 at bit 17, M>>4 at bit 24
-  a.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(g.nb >> 3) << 17) | ((uint32_t)(kBlk >> 4) << 24);
+  return v;
+}
 
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 4) * 8 + 16;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+template <int NB>
+static cudaError_t launch_nb(const TcGemmArgs &g, cudaStream_t s) {
+  TcKernelArgs a;
+  a.Lt = g.Lt;
+  a.zt = g.zt;
+  a.partials = g.partials;
+  a.sk = g.sk;
+  a.chain = tc_chain();
+  // L is streamed once per call when there is one column block; with several, the CTAs of the
+  // other column blocks read the same stage blocks at about the same time -> keep them in L2
+  a.policy_L = g.sk.n_colblk == 1 ? kEvictFirst : kEvictNormal;
+  const uint32_t stage_bytes = 2 * kBlk * kStageK * 4 + 2 * NB * kStageK * 4;
+  const uint32_t budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > 8) stages = 8;
+  a.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
   if (e != cudaSuccess) return e;
-  gemm_tc_kernel<<<g.sk.G, kThreads, smem, s>>>(mLh, mLl, mzh, mzl, a);
+  gemm_tc_kernel<NB><<<g.sk.G, kThreads, smem, s>>>(a);
   return cudaGetLastError();
+}
+
+cudaError_t launch_gemm_tc(const TcGemmArgs &g, cudaStream_t s) {
+  switch (g.nb) {
+    case 16: return launch_nb<16>(g, s);
+    case 32: return launch_nb<32>(g, s);
+    case 48: return launch_nb<48>(g, s);
+    case 64: return launch_nb<64>(g, s);
+    case 80: return launch_nb<80>(g, s);
+    case 96: return launch_nb<96>(g, s);
+    case 112: return launch_nb<112>(g, s);
+    case 128: return launch_nb<128>(g, s);
+  }
+  set_error("tcgen05 contraction: unsupported column block %d", g.nb);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace bndm

@@ -4,6 +4,8 @@
 // Column order: j = n*C + c, n = sample (64^2, 32^2) or 64x64 tile (128^2: n = k*B + b when
 // the source is the caller's image, get_noise_recent.py:131-132; the draw order when the
 // source is a (4B,C,64,64) draw, :138).  Row p = h*64 + w inside the tile (:111).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace bndm {
@@ -33,14 +35,18 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
   }
   const int64_t o = (int64_t)j * kNPix + p;
   if (a.z_raw) st4(a.z_raw + o, v);
-  if (a.z_hi) {
+  if (a.zt) {
     float4 hi, lo;
     tf32_split(v.x, hi.x, lo.x);
     tf32_split(v.y, hi.y, lo.y);
     tf32_split(v.z, hi.z, lo.z);
     tf32_split(v.w, hi.w, lo.w);
-    st4(a.z_hi + o, hi);
-    st4(a.z_lo + o, lo);
+    // stage block (cb, s): rows 0..nb-1 = zh of the block's columns, rows nb..2nb-1 = zl
+    const int cb = j / a.nb, jc = j - cb * a.nb;
+    const int s = p >> 5, kk = p & 31;
+    uint8_t *blk = reinterpret_cast<uint8_t *>(a.zt) + ((size_t)cb * (kNPix / kStageK) + s) * ((size_t)2 * a.nb * kStageK * 4);
+    *reinterpret_cast<float4 *>(blk + sw128_offset(jc, kk)) = hi;
+    *reinterpret_cast<float4 *>(blk + sw128_offset(a.nb + jc, kk)) = lo;
   }
 }
 
@@ -78,22 +84,48 @@ cudaError_t launch_white128(const float *x, float *out, int B, int C, cudaStream
 }
 
 // ---- init-time helpers ---------------------------------------------------------------------
-__global__ void __launch_bounds__(256) split_tf32_kernel(const float *__restrict__ src, float *__restrict__ hi,
-                                                         float *__restrict__ lo, int64_t n4) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-    const float4 v = ld4(src + i * 4);
+// mode 0: hi = rna(v), lo = rna(v - hi) (production).  Experiment modes (BNDM_L_SPLIT_MODE, which
+// probe how tcgen05 kind::tf32 reads a full fp32 operand): 1: hi = v as is, lo = v - trunc(v);
+// 2: hi = v as is, lo = v - rna(v); 3: hi = trunc(v), lo = v - hi (explicit truncation split).
+__device__ __forceinline__ void split_mode(float v, int mode, float &hi, float &lo) {
+  if (mode == 0) { tf32_split(v, hi, lo); return; }
+  const float tr = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  if (mode == 1) { hi = v; lo = __fsub_rn(v, tr); }
+  else if (mode == 2) { hi = v; lo = __fsub_rn(v, tf32_rna(v)); }
+  else { hi = tr; lo = __fsub_rn(v, tr); }
+}
+
+// one CTA per stage block: 128 rows x 32 k of L -> [Lh tile | Ll tile], SWIZZLE_128B image
+__global__ void __launch_bounds__(256) tile_L_kernel(const float *__restrict__ L, float *__restrict__ Lt, int dense, int mode) {
+  const int blk = blockIdx.x;
+  int tile, s;
+  if (dense) {
+    tile = blk >> 7;
+    s = blk & 127;
+  } else {
+    tile = 0;
+    while (2 * (tile + 1) * (tile + 2) <= blk) ++tile;
+    s = blk - 2 * tile * (tile + 1);
+  }
+  uint8_t *dst = reinterpret_cast<uint8_t *>(Lt + (size_t)blk * kLBlockFloats);
+  for (int f = threadIdx.x; f < kBlk * (kStageK / 4); f += blockDim.x) {
+    const int r = f >> 3, kk = (f & 7) << 2;
+    const float4 v = ld4(L + (size_t)(tile * kBlk + r) * kNPix + s * kStageK + kk);
     float4 a, b;
-    tf32_split(v.x, a.x, b.x);
-    tf32_split(v.y, a.y, b.y);
-    tf32_split(v.z, a.z, b.z);
-    tf32_split(v.w, a.w, b.w);
-    st4(hi + i * 4, a);
-    st4(lo + i * 4, b);
+    split_mode(v.x, mode, a.x, b.x);
+    split_mode(v.y, mode, a.y, b.y);
+    split_mode(v.z, mode, a.z, b.z);
+    split_mode(v.w, mode, a.w, b.w);
+    const uint32_t o = sw128_offset(r, kk);
+    *reinterpret_cast<float4 *>(dst + o) = a;
+    *reinterpret_cast<float4 *>(dst + kBlk * kStageK * 4 + o) = b;
   }
 }
 
-cudaError_t launch_split_tf32(const float *src, float *hi, float *lo, int64_t n, cudaStream_t s) {
-  split_tf32_kernel<<<148 * 8, 256, 0, s>>>(src, hi, lo, n / 4);
+cudaError_t launch_tile_L(const float *L, float *Lt, int dense, cudaStream_t s) {
+  int mode = 0;
+  if (const char *e = getenv("BNDM_L_SPLIT_MODE")) mode = atoi(e);
+  tile_L_kernel<<<(unsigned)tile_L_blocks(dense), 256, 0, s>>>(L, Lt, dense, mode);
   return cudaGetLastError();
 }
 

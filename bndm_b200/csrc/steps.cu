@@ -20,30 +20,20 @@ __device__ __forceinline__ float upd2(float x, float d1, float a, float d2, floa
   return __fadd_rn(__fadd_rn(x, __fmul_rn(a, d1)), __fmul_rn(g, d2));
 }
 
-// Scheduled steps keep their step index on the device ({step, tickets} in `state`) so that one
-// captured graph replays for every t.  Each block takes a ticket right after it has read
-// state[0]; the block that draws the last ticket knows every block has read the index and
-// advances it (and publishes the next UNet timestep) while the data path is still streaming
-// -- the atomic's latency hides behind the loads instead of extending the kernel's tail.
-__device__ __forceinline__ int read_step_and_ticket(int *state, bool &is_last) {
-  __shared__ int s_step, s_last;
-  if (threadIdx.x == 0) {
-    const int step = *reinterpret_cast<volatile int *>(&state[0]);
-    __threadfence();
-    const int done = atomicAdd(&state[1], 1);
-    s_step = step;
-    s_last = (done == (int)gridDim.x - 1);
-  }
+// Scheduled steps keep their step index on the device so that one captured graph replays for
+// every t: `state[0]` counts block tickets over the whole sampling run (zeroed by the host
+// before the first step) and a launch of G blocks is step  ticket / G.  One atomic round trip
+// per block, issued after the block's x / d loads so its latency hides behind them; nothing is
+// written that a block of the same launch reads, so there is no end-of-kernel pass.  The block
+// that draws the last ticket of a step publishes the next UNet timestep.
+__device__ __forceinline__ int step_from_ticket(int *state, bool &publishes) {
+  __shared__ int s_ticket;
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&state[0], 1);
   __syncthreads();
-  is_last = s_last != 0;
-  return s_step;
-}
-__device__ __forceinline__ void advance_step(int *state, int step) {
-  if (threadIdx.x == 0) {
-    state[1] = 0;
-    __threadfence();
-    state[0] = step + 1;
-  }
+  const int ticket = s_ticket;
+  const int step = ticket / (int)gridDim.x;
+  publishes = (ticket - step * (int)gridDim.x) == (int)gridDim.x - 1;
+  return step;
 }
 
 // table rows: [step][sample] x {dalpha, dgamma, t_next, 0} (per-sample, like the (B,) coefficient
@@ -52,34 +42,34 @@ template <bool kSched, bool kVec>
 __global__ void __launch_bounds__(256) iadb_step_kernel(IadbArgs a) {
   const bool two = a.Cd == 2 * a.C;
   constexpr int V = kVec ? 4 : 1;
-  const int hwv = a.HW / V;
-  const int64_t total = (int64_t)a.B * a.C * hwv;
-  const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned hwv = (unsigned)(a.HW / V);
+  const unsigned total = (unsigned)a.B * a.C * hwv;          // launcher guarantees < 2^31
+  const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
 
   // issue the first element's loads before touching the schedule: they do not depend on it
   float4 xv0 = make_float4(0.f, 0.f, 0.f, 0.f), u0 = xv0, v0 = xv0;
   if (kVec && first < total) {
-    const int hw = (int)(first % hwv) * V;
-    const int64_t bc = first / hwv;
-    const int b = (int)(bc / a.C), c = (int)(bc - (int64_t)b * a.C);
+    const unsigned bc = first / hwv;
+    const int hw = (int)(first - bc * hwv) * V;
+    const int b = (int)(bc / a.C), c = (int)(bc - b * a.C);
     const int64_t d1 = ((int64_t)b * a.Cd + c) * a.HW + hw;
-    xv0 = *reinterpret_cast<const float4 *>(a.x + bc * a.HW + hw);
+    xv0 = *reinterpret_cast<const float4 *>(a.x + (int64_t)bc * a.HW + hw);
     u0 = ldg4(a.d + d1);
     if (two) v0 = ldg4(a.d + d1 + (int64_t)a.C * a.HW);
   }
 
   const float4 *rows = nullptr;
   int step = 0;
-  bool is_last = false;
+  bool publishes = false;
   if (kSched) {
-    step = read_step_and_ticket(a.state, is_last);
+    step = step_from_ticket(a.state, publishes);
     rows = reinterpret_cast<const float4 *>(a.table) + (int64_t)step * a.B;
   }
 
-  for (int64_t idx = first; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int hw = (int)(idx % hwv) * V;
-    const int64_t bc = idx / hwv;
-    const int b = (int)(bc / a.C), c = (int)(bc - (int64_t)b * a.C);
+  for (unsigned idx = first; idx < total; idx += gridDim.x * blockDim.x) {
+    const unsigned bc = idx / hwv;
+    const int hw = (int)(idx - bc * hwv) * V;
+    const int b = (int)(bc / a.C), c = (int)(bc - b * a.C);
     float da, dg;
     if (kSched) {
       const float4 row = __ldg(rows + b);
@@ -88,7 +78,7 @@ __global__ void __launch_bounds__(256) iadb_step_kernel(IadbArgs a) {
       da = __ldg(a.dalpha + b);
       dg = two ? __ldg(a.dgamma + b) : 0.f;
     }
-    const int64_t xo = bc * a.HW + hw;
+    const int64_t xo = (int64_t)bc * a.HW + hw;
     const int64_t d1 = ((int64_t)b * a.Cd + c) * a.HW + hw;
     const int64_t d2 = d1 + (int64_t)a.C * a.HW;
     if (kVec) {
@@ -114,11 +104,8 @@ __global__ void __launch_bounds__(256) iadb_step_kernel(IadbArgs a) {
       a.x_out[xo] = two ? upd2(xv, a.d[d1], da, a.d[d2], dg) : upd1(xv, a.d[d1], da);
     }
   }
-  if (kSched && is_last) {
-    if (a.t_next_out)
-      for (int b = threadIdx.x; b < a.B; b += blockDim.x) a.t_next_out[b] = __ldg(rows + b).z;
-    advance_step(a.state, step);
-  }
+  if (kSched && publishes && a.t_next_out)
+    for (int b = threadIdx.x; b < a.B; b += blockDim.x) a.t_next_out[b] = __ldg(rows + b).z;
 }
 
 static int grid_for(int64_t work_items, int threads) {
@@ -134,6 +121,7 @@ cudaError_t launch_iadb_step(const IadbArgs &a, bool sched, cudaStream_t s) {
   const bool vec = (a.HW % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.d) |
                                         reinterpret_cast<uintptr_t>(a.x_out)) % 16 == 0);
   const int64_t total = (int64_t)a.B * a.C * (a.HW / (vec ? 4 : 1));
+  if (total >= (int64_t)1 << 31) return cudaErrorInvalidValue;      // 32-bit index math in the kernel
   const int grid = grid_for(total, 256);
   if (sched) {
     if (vec) iadb_step_kernel<true, true><<<grid, 256, 0, s>>>(a);
@@ -157,8 +145,8 @@ __device__ __forceinline__ float ddim1(float x, float e, float z, bool has_noise
 template <bool kVec>
 __global__ void __launch_bounds__(256) ddim_step_kernel(DdimArgs a) {
   int step = 0;
-  bool is_last = false;
-  if (a.state) step = read_step_and_ticket(a.state, is_last);
+  bool publishes = false;
+  if (a.state) step = step_from_ticket(a.state, publishes);
   const float *row = a.coef + 8 * (int64_t)step;
   const float c[5] = {__ldg(row), __ldg(row + 1), __ldg(row + 2), __ldg(row + 3), __ldg(row + 4)};
   const float t_next = __ldg(row + 5);
@@ -179,11 +167,8 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(DdimArgs a) {
       a.x_out[idx] = ddim1(a.x[idx], a.eps[idx], hn ? a.noise[idx] : 0.f, hn, a.clip, c);
     }
   }
-  if (a.state && is_last) {
-    if (a.t_next_out)
-      for (int b = threadIdx.x; b < a.B; b += blockDim.x) a.t_next_out[b] = t_next;
-    advance_step(a.state, step);
-  }
+  if (a.state && publishes && a.t_next_out)
+    for (int b = threadIdx.x; b < a.B; b += blockDim.x) a.t_next_out[b] = t_next;
 }
 
 cudaError_t launch_ddim_step(const DdimArgs &a, cudaStream_t s) {

@@ -107,10 +107,12 @@ int bndm_iadb_step_f32(float *x_out, const float *x, const float *d, const float
 /* Same update driven by a device-resident schedule so that ONE captured CUDA graph of
  * [UNet, step] replays for every t.  `table` is [T][B] rows of 4 floats
  * {dalpha, dgamma, t_next, 0}: per step AND per sample, like the (B,) coefficient tensors the
- * reference forms each step (iadb_bn.py:306-316).  Row used for sample b: table[*step_idx][b].
+ * reference forms each step (iadb_bn.py:306-316).  Row used for sample b: table[step][b].
  * The kernel also fills t_next_out[b] with its row's t_next (the next UNet "timestep" =
- * alpha_start of the following step, iadb_bn.py:311,319) and increments *step_idx.
- * `state` is 2 ints on the device: {step_idx, tickets}, both 0 before the first step.      */
+ * alpha_start of the following step, iadb_bn.py:311,319).
+ * `state` is 2 ints on the device: state[0] counts block tickets over the run (a launch of G
+ * blocks is step ticket / G), state[1] is reserved; zero both before the first step and keep
+ * B, C, HW and the buffers' alignment fixed within a run (they determine G).                */
 int bndm_iadb_step_sched_f32(float *x_out, const float *x, const float *d, const float *table,
                              int *state, float *t_next_out, int B, int C, int HW, int d_channels,
                              void *stream);
