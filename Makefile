@@ -8,7 +8,7 @@ LIB       := bndm_b200/lib/libbndm_b200.so
 
 all: $(LIB)
 
-build/%.o: bndm_b200/csrc/%.cu bndm_b200/csrc/common.cuh include/bndm_b200.h
+build/%.o: bndm_b200/csrc/%.cu $(wildcard bndm_b200/csrc/*.cuh) include/bndm_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 

@@ -36,6 +36,8 @@ SIGNATURES = {
     "bndm_iadb_step_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_iadb_step_sched_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_ddim_step_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, _P]),
+    "bndm_debug_set_trace": (C.c_int, [_P, _P]),
+    "bndm_debug_set_policy": (C.c_int, [C.c_int, C.c_int]),
     "bndm_debug_streamk_check": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "bndm_to_uint8_nhwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }

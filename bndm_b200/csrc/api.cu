@@ -1,6 +1,7 @@
 // C ABI of libbndm_b200.so -- see include/bndm_b200.h for the contract of every entry point.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <new>
 
@@ -29,6 +30,15 @@ static int fail_cuda(cudaError_t e, const char *what) {
     if (e__ != cudaSuccess) return fail_cuda(e__, #expr); \
   } while (0)
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("BNDM_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static bool stream_is_capturing(cudaStream_t s) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(s, &st) != cudaSuccess) {
@@ -45,6 +55,7 @@ using namespace bndm;
 struct bndm_L {
   const float *L = nullptr;     // caller's matrix (bound, not owned)
   float *Lt = nullptr;          // owned: tcgen05 operand, tf32 hi|lo stage blocks (triangular set if L is lower-triangular)
+  float *Lr = nullptr;          // owned: raw fp32 stage blocks of a triangular L (converter variant, 16 KiB each)
   float *Lt_dense = nullptr;    // owned: all 4096 stage blocks of a triangular L, built on the first BNDM_FORCE_DENSE call
   int n = 0;
   int lower_triangular = 0;
@@ -54,13 +65,16 @@ struct bndm_L {
   int req_cols = 0;             // max_columns the workspace was sized for
   size_t cap_partial = 0;
   float *z_raw = nullptr, *zt = nullptr, *partials = nullptr;
+  int *tile_counters = nullptr;   // owned: kMaxTileCounters ints, zero between calls (fused combine)
   int64_t ws_bytes = 0;
   // optional per-launch timing (bndm_profile_enable)
+  unsigned long long *trace = nullptr;   // debug: per-CTA time stamps of the tcgen05 kernel (caller-owned)
   int profile = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int ev_valid = 0;
 };
 
+static const int kMaxTileCounters = 4096;
 static const int kUnitCap = 592;   // most partial tiles a SIMT schedule may produce per column block
 
 static int pad_cols(int n_cols) {
@@ -173,12 +187,20 @@ int bndm_prepare_L(const float *L_dev, int n, int max_columns, void *stream, bnd
   if (h->sm100) {
     const int dense = h->lower_triangular ? 0 : 1;
     e = cudaMalloc(&h->Lt, tile_L_blocks(dense) * kLBlockFloats * sizeof(float));
-    if (e == cudaSuccess) e = launch_tile_L(L_dev, h->Lt, dense, s);
+    if (e == cudaSuccess) e = launch_tile_L(L_dev, h->Lt, dense, 0, s);
+    if (e == cudaSuccess && !dense) {
+      e = cudaMalloc(&h->Lr, tile_L_blocks(0) * (kLBlockFloats / 2) * sizeof(float));
+      if (e == cudaSuccess) e = launch_tile_L(L_dev, h->Lr, 0, 1, s);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { bndm_free_L(h); return fail_cuda(e, "tf32 split / tiling of L"); }
   }
   int rc = alloc_ws(h, max_columns);
   if (rc != BNDM_OK) { bndm_free_L(h); return rc; }
+  e = cudaMalloc(&h->tile_counters, kMaxTileCounters * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemsetAsync(h->tile_counters, 0, kMaxTileCounters * sizeof(int), s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) { bndm_free_L(h); return fail_cuda(e, "tile counters"); }
   *out = h;
   return BNDM_OK;
 }
@@ -215,6 +237,17 @@ int bndm_profile_last_ms(bndm_L *h, float *pack_ms, float *gemm_ms, float *epilo
   return BNDM_OK;
 }
 
+int bndm_debug_set_policy(int fused_combine, int raw_L) {
+  tc_set_policy(fused_combine, raw_L);
+  return BNDM_OK;
+}
+
+int bndm_debug_set_trace(bndm_L *h, unsigned long long *trace_dev) {
+  if (!h) { set_error("null handle"); return BNDM_ERR_ARG; }
+  h->trace = trace_dev;
+  return BNDM_OK;
+}
+
 int bndm_free_L(bndm_L *h) {
   if (!h) return BNDM_OK;
   for (int i = 0; i < 4; ++i)
@@ -222,6 +255,8 @@ int bndm_free_L(bndm_L *h) {
   free_ws(h);
   cudaFree(h->Lt);
   cudaFree(h->Lt_dense);
+  cudaFree(h->Lr);
+  cudaFree(h->tile_counters);
   delete h;
   return BNDM_OK;
 }
@@ -306,22 +341,48 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
     // K1b (tcgen05, persistent stream-K) -> K1c (ordered combine + lerp + layout)
     TcGemmArgs g;
     g.Lt = h->Lt;
+    g.raw_L = 0;
+    if (!dense && h->Lr && tc_raw_L(nb, sk.n_colblk)) {
+      g.Lt = h->Lr;
+      g.raw_L = 1;
+    }
     if (dense && h->lower_triangular) {
       // BNDM_FORCE_DENSE on a triangular L (testing): needs the full block set, built once
       if (!h->Lt_dense) {
         if (stream_is_capturing(s)) { set_error("dense operand copy requested during stream capture"); return BNDM_ERR_WORKSPACE; }
         CK(cudaMalloc(&h->Lt_dense, tile_L_blocks(1) * kLBlockFloats * sizeof(float)));
-        CK(launch_tile_L(h->L, h->Lt_dense, 1, s));
+        CK(launch_tile_L(h->L, h->Lt_dense, 1, 0, s));
       }
       g.Lt = h->Lt_dense;
     }
     g.zt = h->zt;
+    g.trace = h->trace;
+    // small column blocks: the combine is fused into the contraction (the last CTA to finish a
+    // row tile sums its partial tiles); large ones keep the wide combine kernel
+    const bool fused = tc_fused_combine(nb) && sk.n_colblk * sk.n_tiles <= kMaxTileCounters;
+    g.tile_counters = h->tile_counters;
+    g.z_cols = z_cols;
+    g.gamma = gamma;
+    g.out = fused ? out : nullptr;
+    g.out_bn = out_bn;
+    g.out_wn = out_wn;
+    g.n_cols = n_cols;
+    g.B = B;
+    g.C = C;
+    g.res_mode = mode;
     g.partials = h->partials;
     g.n_cols_pad = n_cols_pad;
     g.nb = nb;
     g.sk = sk;
     CK(launch_gemm_tc(g, s));
     if (prof) CK(cudaEventRecord(h->ev[2], s));
+    if (fused) {
+      if (prof) {
+        CK(cudaEventRecord(h->ev[3], s));
+        h->ev_valid = 1;
+      }
+      return BNDM_OK;
+    }
     CombineArgs cb;
     cb.partials = h->partials;
     cb.z_cols = z_cols;

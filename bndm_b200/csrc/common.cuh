@@ -16,6 +16,31 @@ enum ResMode : int { kRes64 = 0, kRes32 = 1, kRes128 = 2 };
 
 void set_error(const char *fmt, ...);
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------
+// The kernels of one get_noise call (pack -> contraction -> combine) are launched with
+// programmatic stream serialisation: a kernel may start while its predecessor is still
+// running (launch latency, barrier/TMEM set-up and the L loads of the contraction overlap the
+// predecessor's tail) and calls pdl_wait() before it touches anything a predecessor wrote or
+// still reads.  pdl_wait() returns once the preceding grid has completed and flushed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // BNDM_NO_PDL=1 turns it off (A/B measurements)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- the triangular unit schedule, shared by GEMM kernels and the epilogue ---------------
 // Row tile i covers rows [128 i, 128 i + 128); it needs k-blocks [0, kb(i)) with
 // kb(i) = i + 1 (lower-triangular L) or 32 (dense).  The k range is cut in chunks of `kc`
@@ -82,7 +107,7 @@ cudaError_t launch_epilogue(const EpilogueArgs &a, cudaStream_t s);
 cudaError_t launch_white128(const float *x, float *out, int B, int C, cudaStream_t s);
 // L -> stage blocks [Lh tile | Ll tile] in the SWIZZLE_128B shared-memory image (noise_gemm_tc.cu);
 // n_blocks = 2112 (lower-triangular, blocks of row tile i start at 2 i (i + 1)) or 4096 (dense)
-cudaError_t launch_tile_L(const float *L, float *Lt, int dense, cudaStream_t s);
+cudaError_t launch_tile_L(const float *L, float *Lt, int dense, int raw, cudaStream_t s);
 inline size_t tile_L_blocks(int dense) { return dense ? (size_t)kNumBlk * (kNPix / kStageK) : (size_t)2 * kNumBlk * (kNumBlk + 1); }
 constexpr size_t kLBlockFloats = 2 * kBlk * kStageK;   // 32 KiB per stage block
 
@@ -95,7 +120,10 @@ cudaError_t launch_tri_check(const float *L, int n, int *flag_dev, cudaStream_t 
 // ---- stream-K schedule of the tensor-core contraction (see noise_gemm_tc.cu) ---------------
 // Stage = (row tile, 32 k values, column block).  Row tile i owns 4 (i + 1) stages (lower-
 // triangular L) or 128 (dense); the W stages of all column blocks are cut into G contiguous
-// equal ranges, one per CTA.  Shared by the GEMM kernel and the combine kernel.
+// equal ranges, one per CTA.  Inside a column block the row tiles are visited from the LAST
+// (longest) to the first, so the work that finishes last belongs to the shortest tiles and the
+// fused combine of the big tiles overlaps the rest of the kernel.  Shared by the GEMM kernel
+// and the combine kernel.
 struct StreamK {
   int n_tiles;    // row tiles: 32, or 16 for the 32^2 branch (rows with h >= 32 are never stored)
   int dense;      // 0: lower-triangular, 1: dense
@@ -103,23 +131,28 @@ struct StreamK {
   int G;          // CTAs = min(#SMs, W)
   int Stot;       // stages per column block
   int W;          // n_colblk * Stot
+  // stages of row tiles [0, i): also the index of tile i's first stage block in Lt
   __host__ __device__ int cum(int i) const { return dense ? (kNPix / kStageK) * i : 2 * i * (i + 1); }
   __host__ __device__ int cta_begin(int c) const { return (int)((int64_t)c * W / G); }
   __host__ __device__ int cta_of(int g) const { return (int)((((int64_t)g + 1) * G - 1) / W); }
-  __host__ __device__ int tile_begin(int cb, int tile) const { return cb * Stot + cum(tile); }
-  __host__ __device__ int tile_end(int cb, int tile) const { return cb * Stot + cum(tile + 1); }
+  __host__ __device__ int tile_begin(int cb, int tile) const { return cb * Stot + Stot - cum(tile + 1); }
+  __host__ __device__ int tile_end(int cb, int tile) const { return cb * Stot + Stot - cum(tile); }
   __host__ __device__ void decode(int g, int &cb, int &tile, int &s) const {
     cb = g / Stot;
     const int r = g - cb * Stot;
+    const int a = Stot - 1 - r;          // position in ascending-tile order
     int i = 0;
-    while (cum(i + 1) <= r) ++i;
+    while (cum(i + 1) <= a) ++i;
     tile = i;
-    s = r - cum(i);
+    s = r - (Stot - cum(i + 1));         // stage inside the tile, ascending k
   }
-  // partial-tile slot of the segment CTA `cta` computes inside (cb, tile): cta + tile index is
+  // partial-tile slot of the segment CTA `cta` computes inside (cb, tile): cta + visit index is
   // strictly increasing along the global stage order, hence unique per segment
-  __host__ __device__ int slot(int cta, int cb, int tile) const { return cta + cb * n_tiles + tile; }
+  __host__ __device__ int slot(int cta, int cb, int tile) const { return cta + cb * n_tiles + (n_tiles - 1 - tile); }
   __host__ __device__ int n_slots() const { return G + n_colblk * n_tiles - 1; }
+  // CTAs that contribute a segment to (cb, tile): first .. last, ascending k
+  __host__ __device__ int first_cta(int cb, int tile) const { return cta_of(tile_begin(cb, tile)); }
+  __host__ __device__ int last_cta(int cb, int tile) const { return cta_of(tile_end(cb, tile) - 1); }
 };
 inline StreamK make_streamk(int n_tiles, int dense, int n_colblk, int num_sms) {
   StreamK k;
@@ -134,15 +167,27 @@ inline StreamK make_streamk(int n_tiles, int dense, int n_colblk, int num_sms) {
 
 struct TcGemmArgs {
   const float *Lt;            // stage blocks of L (launch_tile_L), triangular or dense per sk.dense
+  int raw_L;                  // Lt holds raw fp32 16 KiB blocks (converter variant) instead of hi|lo 32 KiB blocks
   const float *zt;            // stage blocks of z (launch_pack)
   float *partials;            // [n_slots][nb][128]
   int n_cols_pad;             // n_colblk * nb
   int nb;                     // columns per column block (multiple of 16, <= 128)
+  unsigned long long *trace;  // debug time stamps [cta][24] or null
   StreamK sk;
+  // fused combine (the last CTA to finish a row tile sums its partial tiles and writes the
+  // outputs; no combine kernel): out == null -> partial tiles only
+  int *tile_counters;         // [n_colblk][n_tiles], zero between calls (self-resetting)
+  const float *z_cols;        // packed raw columns [.][4096] (white values)
+  const float *gamma;         // [B] or null
+  float *out, *out_bn, *out_wn;
+  int n_cols, B, C, res_mode;
 };
 cudaError_t launch_gemm_tc(const TcGemmArgs &a, cudaStream_t s);
 int tc_pick_nb(int n_cols);   // column block for a given column count
 int tc_num_sms();
+bool tc_fused_combine(int nb);
+bool tc_raw_L(int nb, int n_colblk);   // policy: raw-L converter variant for this shape?
+void tc_set_policy(int fused, int raw);   // policy: combine fused into the contraction for this column block?
 
 // combine of the stream-K partials + everything get_noise_v2 does after the matmul
 struct CombineArgs {

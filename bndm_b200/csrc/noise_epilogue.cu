@@ -9,100 +9,52 @@
 //   epilogue_kernel  partials of the SIMT reference contraction, [unit][column][128 rows]
 // Both are bit-reproducible run to run (fixed order, no atomics).
 #include "common.cuh"
+#include "out_map.cuh"
 
 namespace bndm {
-
-struct OutMap {
-  const float *z_cols;
-  const float *gamma;
-  float *out, *out_bn, *out_wn;
-  int B, C, res_mode;
-};
-
-// Writes 4 consecutive pixels p..p+3 (same image row: p % 4 == 0) of GEMM column j.
-__device__ __forceinline__ void emit4(const OutMap &m, int j, int p, float4 bn) {
-  const int h = p >> 6, w = p & 63;
-  int64_t dst;
-  float4 wn;
-  int b;
-  if (m.res_mode == kRes64) {
-    b = j / m.C;
-    dst = (int64_t)j * kNPix + p;
-    wn = *reinterpret_cast<const float4 *>(m.z_cols + (int64_t)j * kNPix + p);
-  } else if (m.res_mode == kRes32) {
-    if (h >= 32 || w >= 32) return;       // cropped away (:97-99)
-    b = j / m.C;
-    dst = (int64_t)j * 1024 + h * 32 + w;
-    wn = *reinterpret_cast<const float4 *>(m.z_cols + (int64_t)j * kNPix + p);
-  } else {
-    const int n = j / m.C, c = j - n * m.C;
-    b = n >> 2;                           // (4B,...) re-viewed as (B,4,...): n = 4 b' + k'
-    const int k = n & 3;
-    const int r0 = (k & 1) * kTile, c0 = (k >> 1) * kTile;     // noise_padding placement
-    dst = (((int64_t)b * m.C + c) * 128 + r0 + h) * 128 + c0 + w;
-    // (n, pixel, channel) memory re-read as (n, channel, pixel): flat f = c*4096 + p
-    const float *zn = m.z_cols + (int64_t)n * m.C * kNPix;
-    float t[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int f = c * kNPix + p + e;
-      const int cs = f % m.C, ps = f / m.C;
-      t[e] = zn[(int64_t)cs * kNPix + ps];
-    }
-    wn = make_float4(t[0], t[1], t[2], t[3]);
-  }
-  float4 o = bn;
-  if (m.gamma) {
-    const float g = m.gamma[b];
-    const float gi = __fsub_rn(1.0f, g);
-    o.x = __fadd_rn(__fmul_rn(bn.x, gi), __fmul_rn(wn.x, g));
-    o.y = __fadd_rn(__fmul_rn(bn.y, gi), __fmul_rn(wn.y, g));
-    o.z = __fadd_rn(__fmul_rn(bn.z, gi), __fmul_rn(wn.z, g));
-    o.w = __fadd_rn(__fmul_rn(bn.w, gi), __fmul_rn(wn.w, g));
-  }
-  *reinterpret_cast<float4 *>(m.out + dst) = o;
-  if (m.out_bn) *reinterpret_cast<float4 *>(m.out_bn + dst) = bn;
-  if (m.out_wn) *reinterpret_cast<float4 *>(m.out_wn + dst) = wn;
-}
-
-__device__ __forceinline__ float4 add4(float4 a, float4 b) {
-  return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
-}
 
 // ---- tensor-core path -----------------------------------------------------------------------
 // block = 32 row-quads x 8 columns; grid = (row tiles, ceil(n_cols / 8))
 constexpr int kCombCols = 8;
 
 __global__ void __launch_bounds__(256) combine_kernel(CombineArgs a) {
+  pdl_launch_dependents();
+  // everything that does not touch memory first: under PDL this overlaps the contraction's tail
   const int tile = blockIdx.x;
   const int rq = threadIdx.x & 31;                 // rows 4 rq .. 4 rq + 3 of the tile
   const int j = blockIdx.y * kCombCols + (threadIdx.x >> 5);
-  if (j >= a.n_cols) return;
-  const int cb = j / a.nb, jc = j - cb * a.nb;
+  const bool live = j < a.n_cols;
+  const int jj = live ? j : 0;
+  const int cb = jj / a.nb, jc = jj - cb * a.nb;
   const StreamK sk = a.sk;
-  const int c_first = sk.cta_of(sk.tile_begin(cb, tile));
-  const int c_last = sk.cta_of(sk.tile_end(cb, tile) - 1);
+  const int c_first = sk.first_cta(cb, tile);
+  const int n_seg = sk.last_cta(cb, tile) - c_first + 1;
   const int64_t slot_stride = (int64_t)a.nb * kBlk;
-  const float *P = a.partials + (int64_t)sk.slot(c_first, cb, tile) * slot_stride + (int64_t)jc * kBlk + rq * 4;
-  float4 bn = *reinterpret_cast<const float4 *>(P);
-  const int n = c_last - c_first;
-  int s = 1;
-  for (; s + 4 <= n + 1; s += 4) {                 // batches of 4 independent loads, summed in order
-    const float4 v0 = *reinterpret_cast<const float4 *>(P + (int64_t)s * slot_stride);
-    const float4 v1 = *reinterpret_cast<const float4 *>(P + (int64_t)(s + 1) * slot_stride);
-    const float4 v2 = *reinterpret_cast<const float4 *>(P + (int64_t)(s + 2) * slot_stride);
-    const float4 v3 = *reinterpret_cast<const float4 *>(P + (int64_t)(s + 3) * slot_stride);
-    bn = add4(add4(add4(add4(bn, v0), v1), v2), v3);
-  }
-  for (; s <= n; ++s) bn = add4(bn, *reinterpret_cast<const float4 *>(P + (int64_t)s * slot_stride));
+  const float4 *P = reinterpret_cast<const float4 *>(a.partials + (int64_t)sk.slot(c_first, cb, tile) * slot_stride +
+                                                     (int64_t)jc * kBlk + rq * 4);
+  const int64_t stride4 = slot_stride / 4;
   const OutMap m{a.z_cols, a.gamma, a.out, a.out_bn, a.out_wn, a.B, a.C, a.res_mode};
-  emit4(m, j, tile * kBlk + rq * 4, bn);
+  pdl_wait();                   // partial tiles of the contraction are complete and visible
+  if (!live) return;
+  // one round trip for the common case: the white / gamma loads and up to 8 partial tiles are
+  // all in flight together; the sum runs in ascending-k order (bit-reproducible)
+  const OutPos4 q = locate4(m, j, tile * kBlk + rq * 4);
+  float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s0 = 0; s0 < n_seg; s0 += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      v[g] = (s0 + g < n_seg) ? __ldcg(P + (int64_t)(s0 + g) * stride4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      if (s0 + g < n_seg) bn = (s0 + g == 0) ? v[g] : add4(bn, v[g]);
+  }
+  store4(m, q, bn);
 }
 
 cudaError_t launch_combine(const CombineArgs &a, cudaStream_t s) {
   dim3 grid(a.sk.n_tiles, (a.n_cols + kCombCols - 1) / kCombCols);
-  combine_kernel<<<grid, 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(combine_kernel, grid, dim3(256), 0, s, a);
 }
 
 // ---- SIMT reference path ------------------------------------------------------------------------

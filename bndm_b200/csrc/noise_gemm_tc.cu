@@ -37,11 +37,13 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "out_map.cuh"
 
 namespace bndm {
 
 constexpr int kUmmaK = 8;                         // tf32: 32 bytes of K per tcgen05.mma
 constexpr int kThreads = 192;
+constexpr int kThreadsRaw = 320;                  // + 4 converter warps
 constexpr uint32_t kSpinLimit = 1u << 27;         // bounded spins: a protocol bug traps instead of hanging the GPU
 
 // L2 eviction-priority policies for bulk loads (createpolicy encodings)
@@ -147,8 +149,20 @@ struct TcKernelArgs {
   int stages;         // smem ring depth
   int chain;          // stages per TMEM accumulation chain
   uint64_t policy_L;
+  unsigned long long *trace;   // debug: [cta][24] time stamps / cycle sums (null in production)
   StreamK sk;
+  // fused combine (out != null): the CTA that completes a row tile's last segment sums the
+  // tile's partial tiles in ascending-k order and writes the outputs
+  int *tile_counters;
+  OutMap om;
+  int n_cols;
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // One (<= chain)-stage piece of a segment; every role walks the same sequence.
 struct ChainWalk {
@@ -178,9 +192,15 @@ struct ChainWalk {
   }
 };
 
-template <int NB>
-__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcKernelArgs a) {
-  constexpr uint32_t kLBlockBytes = 2 * kBlk * kStageK * 4;       // 32 KiB: Lh tile | Ll tile
+// kRawL: the L stage blocks in HBM hold the raw fp32 tile only (16 KiB instead of 32): the tensor
+// core ignores the 13 low mantissa bits of an fp32 operand (measured, tools/exp_split.py), so the
+// raw tile IS the hi operand, and four converter warps (6..9) write  Ll = L - trunc_tf32(L)
+// (exact in fp32) next to it in shared memory before the issuer may read the stage.  Halves the
+// bytes streamed from HBM; used when one column block covers the call (HBM-bound regime).
+template <int NB, bool kRawL>
+__global__ void __launch_bounds__(kRawL ? kThreadsRaw : kThreads, 1) gemm_tc_kernel(const TcKernelArgs a) {
+  constexpr uint32_t kLBlockBytes = 2 * kBlk * kStageK * 4;       // 32 KiB in smem: Lh tile | Ll tile
+  constexpr uint32_t kLLoadBytes = kRawL ? kLBlockBytes / 2 : kLBlockBytes;     // bytes per stage from HBM
   constexpr uint32_t kZBlockBytes = 2 * NB * kStageK * 4;         // zh rows | zl rows
   constexpr uint32_t kStageBytes = kLBlockBytes + kZBlockBytes;
   constexpr uint32_t kBufCols = 2 * NB;                           // main | correction
@@ -193,16 +213,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcKernelArgs
   uint64_t *empty_bar = full_bar + a.stages;
   uint64_t *acc_full = empty_bar + a.stages;      // [2]
   uint64_t *acc_empty = acc_full + 2;             // [2]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  uint64_t *conv_bar = acc_empty + 2;             // [stages] (kRawL): Ll tile written, stage ready for the issuer
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(conv_bar + a.stages);
+  volatile int *combine_flag = reinterpret_cast<volatile int *>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
+  unsigned long long *tr = a.trace ? a.trace + (size_t)cta * 24 : nullptr;
+  if (tr && threadIdx.x == 0) { tr[0] = gtime(); tr[1] = clock64(); }
 
+  pdl_launch_dependents();                // the combine kernel may be scheduled; it waits for this grid
+  if (warp == 0 && lane > 0 && cta < 2 && a.om.out != nullptr && a.om.gamma != nullptr) {
+    // fused combine reads gamma at the very end, when the DRAM queues are full of L traffic and a
+    // miss costs several microseconds (measured): pull its few lines into L2 now (hint only)
+    for (int i = (lane - 1) * 32; i < a.om.B; i += 31 * 32)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(a.om.gamma + i));
+  }
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], 4);                 // one arrival per converter warp
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
@@ -215,22 +247,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcKernelArgs
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tr && threadIdx.x == 0) tr[2] = clock64();
 
   if (warp == 0) {
     // ================= producer: one bulk copy per operand per stage =================
     if (lane == 0) {
+      // L is never written by a preceding kernel: its loads go out at once; the z blocks are
+      // the pack kernel's output, so the first of them waits for that grid (PDL)
+      bool z_ready = false;
       ChainWalk w(a.sk, cta, a.chain);
       int it = 0;
       while (w.next()) {
-        const float *Lblk = a.Lt + (size_t)(a.sk.cum(w.tile) + w.s0) * (kLBlockBytes / 4);
+        const float *Lblk = a.Lt + (size_t)(a.sk.cum(w.tile) + w.s0) * (kLLoadBytes / 4);
         const float *zblk = a.zt + (size_t)(w.cb * (kNPix / kStageK) + w.s0) * (kZBlockBytes / 4);
         for (int n = 0; n < w.n; ++n, ++it) {
           const int st = it % a.stages;
           const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
+          const long long t0 = tr ? clock64() : 0;
           mbar_wait(&empty_bar[st], ph ^ 1u);
+          if (tr) tr[20] += (unsigned long long)(clock64() - t0);
           const uint32_t sa = smem_u32(base + (size_t)st * kStageBytes);
-          mbar_expect_tx(&full_bar[st], kStageBytes);
-          bulk_load(sa, Lblk + (size_t)n * (kLBlockBytes / 4), kLBlockBytes, &full_bar[st], a.policy_L);
+          mbar_expect_tx(&full_bar[st], kLLoadBytes + kZBlockBytes);
+          bulk_load(sa, Lblk + (size_t)n * (kLLoadBytes / 4), kLLoadBytes, &full_bar[st], a.policy_L);
+          if (!z_ready) {
+            pdl_wait();
+            z_ready = true;
+          }
           bulk_load(sa + kLBlockBytes, zblk + (size_t)n * (kZBlockBytes / 4), kZBlockBytes, &full_bar[st], kEvictLast);
         }
       }
@@ -249,8 +291,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcKernelArgs
         for (int n = 0; n < w.n; ++n, ++it) {
           const int st = it % a.stages;
           const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
-          mbar_wait(&full_bar[st], ph);
+          const long long t0 = tr ? clock64() : 0;
+          mbar_wait(kRawL ? &conv_bar[st] : &full_bar[st], ph);
           tc_fence_after();
+          if (tr) tr[18] += (unsigned long long)(clock64() - t0);
+          if (tr && it == 0) tr[3] = clock64();
           const uint32_t sa = smem_u32(base + (size_t)st * kStageBytes);
           const uint64_t dAh = umma_desc(sa);
           const uint64_t dAl = umma_desc(sa + kLBlockBytes / 2);
@@ -265,12 +310,46 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcKernelArgs
         }
         umma_commit(&acc_full[buf]);         // this chain's accumulators are complete
       }
+      if (tr) tr[4] = clock64();
+    }
+  } else if (kRawL && warp >= 6) {
+    // ================= converter: Ll = L - trunc_tf32(L), 8 x 16 bytes per thread per stage =================
+    const int t = threadIdx.x - 192;
+    ChainWalk w(a.sk, cta, a.chain);
+    int it = 0;
+    while (w.next()) {
+      for (int n = 0; n < w.n; ++n, ++it) {
+        const int st = it % a.stages;
+        const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
+        const long long t0 = (tr && t == 0) ? clock64() : 0;
+        mbar_wait(&full_bar[st], ph);
+        const long long t1 = (tr && t == 0) ? clock64() : 0;
+        const float4 *src = reinterpret_cast<const float4 *>(base + (size_t)st * kStageBytes) + t;
+        float4 *dst = reinterpret_cast<float4 *>(base + (size_t)st * kStageBytes + kLBlockBytes / 2) + t;
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = src[i * 128];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 lo;
+          lo.x = __fsub_rn(v[i].x, __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u));
+          lo.y = __fsub_rn(v[i].y, __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u));
+          lo.z = __fsub_rn(v[i].z, __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u));
+          lo.w = __fsub_rn(v[i].w, __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u));
+          dst[i * 128] = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_bar[st]);
+        if (tr && t == 0) { tr[17] += (unsigned long long)(t1 - t0); tr[16] += (unsigned long long)(clock64() - t1); }
+      }
     }
   } else {
     // ================= epilogue: TMEM -> fp32 running sums -> partial tile =================
     const int q = warp & 3;               // TMEM lane quarter this warp may touch
     const int r = q * 32 + lane;          // row inside the tile
     float acc[NB];
+    pdl_wait();                           // the previous call's combine is done reading the partial tiles
     ChainWalk w(a.sk, cta, a.chain);
     for (int ch = 0; w.next(); ++ch) {
       const int buf = ch & 1;
@@ -295,11 +374,74 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcKernelArgs
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       if (w.last) {
-        float *P = a.partials + ((int64_t)a.sk.slot(cta, w.cb, w.tile) * NB) * kBlk + r;
+        const int c_first = a.sk.first_cta(w.cb, w.tile), c_last = a.sk.last_cta(w.cb, w.tile);
+        const int col0 = w.cb * NB;
+        const int p = w.tile * kBlk + r;
+        if (a.om.out != nullptr && c_first == c_last) {
+          // the whole row tile was computed here: straight from the registers to the outputs
 #pragma unroll
-        for (int c = 0; c < NB; ++c) P[(int64_t)c * kBlk] = acc[c];          // 32 lanes -> 128 B rows
+          for (int c = 0; c < NB; c += 16)
+            if (col0 + c < a.n_cols) emit_cols<16>(a.om, col0 + c, a.n_cols, p, acc + c);
+        } else {
+          const int64_t slot_stride = (int64_t)NB * kBlk;
+          float *P = a.partials + (int64_t)a.sk.slot(cta, w.cb, w.tile) * slot_stride + r;
+#pragma unroll
+          for (int c = 0; c < NB; ++c) P[(int64_t)c * kBlk] = acc[c];          // 32 lanes -> 128 B rows
+          if (a.om.out != nullptr) {
+            // ticket: the last of the tile's (c_last - c_first + 1) contributors combines
+            if (tr && threadIdx.x == 64) tr[8] = clock64();
+            __threadfence();
+            if (tr && threadIdx.x == 64) tr[9] = clock64();
+            asm volatile("bar.sync 1, 128;" ::: "memory");                     // the 4 epilogue warps
+            if (threadIdx.x == 64) {
+              int *cnt = a.tile_counters + w.cb * a.sk.n_tiles + w.tile;
+              const int old = atomicAdd(cnt, 1);
+              const int is_last = (old == c_last - c_first);
+              if (is_last) *cnt = 0;                                           // ready for the next call
+              *combine_flag = is_last;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (tr && threadIdx.x == 64) tr[10] = clock64();
+            if (*combine_flag) {
+              __threadfence();
+              if (tr && threadIdx.x == 64) { tr[11] = clock64(); tr[14] = (unsigned long long)(c_last - c_first + 1); }
+              const float *Q = a.partials + (int64_t)a.sk.slot(c_first, w.cb, w.tile) * slot_stride + r;
+              const int n_seg = c_last - c_first + 1;
+              // CB columns x SG segments (= 64) independent L2 loads in flight per thread, then the
+              // adds in ascending-k order (the order is what makes the result reproducible)
+              // (fewer for the big column blocks, whose running sums already fill the register file;
+              // they use the wide combine kernel by default)
+              constexpr int CB = NB <= 32 ? 16 : 8, SG = NB <= 32 ? 4 : 2;
+              for (int c = 0; c < NB; c += CB) {
+                if (col0 + c >= a.n_cols) break;
+                float v[CB];
+#pragma unroll
+                for (int e = 0; e < CB; ++e) v[e] = 0.0f;
+                for (int s0 = 0; s0 < n_seg; s0 += SG) {
+                  float u[SG][CB];
+#pragma unroll
+                  for (int g = 0; g < SG; ++g)
+#pragma unroll
+                    for (int e = 0; e < CB; ++e)
+                      u[g][e] = (s0 + g < n_seg) ? __ldcg(Q + (int64_t)(s0 + g) * slot_stride + (int64_t)(c + e) * kBlk) : 0.0f;
+#pragma unroll
+                  for (int g = 0; g < SG; ++g)
+                    if (s0 + g < n_seg) {
+#pragma unroll
+                      for (int e = 0; e < CB; ++e) v[e] = (s0 + g == 0) ? u[g][e] : __fadd_rn(v[e], u[g][e]);
+                    }
+                }
+                if (tr && threadIdx.x == 64) tr[12] = clock64();
+                emit_cols<CB>(a.om, col0 + c, a.n_cols, p, v);
+              }
+              if (tr && threadIdx.x == 64) tr[13] = clock64();
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");                     // combine_flag is reused
+          }
+        }
       }
     }
+    if (tr && threadIdx.x == 64) tr[5] = clock64();
   }
 
   tc_fence_before();
@@ -308,6 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const TcKernelArgs
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
+  if (tr && threadIdx.x == 0) { tr[6] = clock64(); tr[7] = gtime(); }
 }
 
 // --------------------------------------------------------------------------------- host
@@ -343,6 +486,22 @@ int tc_num_sms() {
   return n;
 }
 
+// Policy knobs: -1 = default rule, 0 = off, 1 = on.  Initialised from BNDM_TC_FUSED / BNDM_TC_RAWL,
+// overridable at run time through bndm_debug_set_policy (tests sweep every variant).
+static int g_policy_fused = -2, g_policy_raw = -2;
+static int env_policy(const char *name) {
+  const char *e = getenv(name);
+  return e ? (e[0] == '1' ? 1 : 0) : -1;
+}
+void tc_set_policy(int fused, int raw) {
+  g_policy_fused = fused;
+  g_policy_raw = raw;
+}
+bool tc_fused_combine(int nb) {
+  if (g_policy_fused == -2) g_policy_fused = env_policy("BNDM_TC_FUSED");
+  return g_policy_fused < 0 ? false : g_policy_fused == 1;   // default off: see DESIGN.md (tail latency)
+}
+
 static int tc_chain() {
   static int v = 0;
   if (!v) {
@@ -355,7 +514,7 @@ static int tc_chain() {
   return v;
 }
 
-template <int NB>
+template <int NB, bool kRawL>
 static cudaError_t launch_nb(const TcGemmArgs &g, cudaStream_t s) {
   TcKernelArgs a;
   a.Lt = g.Lt;
@@ -363,34 +522,63 @@ static cudaError_t launch_nb(const TcGemmArgs &g, cudaStream_t s) {
   a.partials = g.partials;
   a.sk = g.sk;
   a.chain = tc_chain();
+  a.trace = g.trace;
+  a.tile_counters = g.tile_counters;
+  a.om = OutMap{g.z_cols, g.gamma, g.out, g.out_bn, g.out_wn, g.B, g.C, g.res_mode};
+  a.n_cols = g.n_cols;
   // L is streamed once per call when there is one column block; with several, the CTAs of the
   // other column blocks read the same stage blocks at about the same time -> keep them in L2
   a.policy_L = g.sk.n_colblk == 1 ? kEvictFirst : kEvictNormal;
   const uint32_t stage_bytes = 2 * kBlk * kStageK * 4 + 2 * NB * kStageK * 4;
   const uint32_t budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
+  // One column block (cold L2): the kernel is HBM-bound and more than ~100 KiB in flight per SM
+  // only lengthens the DRAM queue, i.e. spreads the time the first operands land and with it
+  // the CTAs' finishing times (measured).  Several column blocks: half the L loads hit in L2 and
+  // shared-memory bandwidth bounds a stage -> as deep as fits.
   int stages = (int)(budget / stage_bytes);
   if (stages > 8) stages = 8;
+  if (g.sk.n_colblk == 1 && stages > (kRawL ? 5 : 3)) stages = kRawL ? 5 : 3;
+  if (const char *e = getenv("BNDM_TC_STAGES")) {     // experiment knob: shallower ring
+    const int x = atoi(e);
+    const int fit = (int)(budget / stage_bytes) < 8 ? (int)(budget / stage_bytes) : 8;
+    if (x >= 1 && x <= fit) stages = x;
+  }
   a.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + (2 * stages + 4) * 8 + 16;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + (3 * stages + 4) * 8 + 16;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NB, kRawL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
   if (e != cudaSuccess) return e;
-  gemm_tc_kernel<NB><<<g.sk.G, kThreads, smem, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(gemm_tc_kernel<NB, kRawL>, dim3(g.sk.G), dim3(kRawL ? kThreadsRaw : kThreads), smem, s, a);
 }
 
 cudaError_t launch_gemm_tc(const TcGemmArgs &g, cudaStream_t s) {
+  if (g.raw_L) {
+    switch (g.nb) {
+      case 16: return launch_nb<16, true>(g, s);
+      case 32: return launch_nb<32, true>(g, s);
+      case 48: return launch_nb<48, true>(g, s);
+      case 64: return launch_nb<64, true>(g, s);
+    }
+    set_error("tcgen05 contraction (raw L): unsupported column block %d", g.nb);
+    return cudaErrorInvalidValue;
+  }
   switch (g.nb) {
-    case 16: return launch_nb<16>(g, s);
-    case 32: return launch_nb<32>(g, s);
-    case 48: return launch_nb<48>(g, s);
-    case 64: return launch_nb<64>(g, s);
-    case 80: return launch_nb<80>(g, s);
-    case 96: return launch_nb<96>(g, s);
-    case 112: return launch_nb<112>(g, s);
-    case 128: return launch_nb<128>(g, s);
+    case 16: return launch_nb<16, false>(g, s);
+    case 32: return launch_nb<32, false>(g, s);
+    case 48: return launch_nb<48, false>(g, s);
+    case 64: return launch_nb<64, false>(g, s);
+    case 80: return launch_nb<80, false>(g, s);
+    case 96: return launch_nb<96, false>(g, s);
+    case 112: return launch_nb<112, false>(g, s);
+    case 128: return launch_nb<128, false>(g, s);
   }
   set_error("tcgen05 contraction: unsupported column block %d", g.nb);
   return cudaErrorInvalidValue;
+}
+
+bool tc_raw_L(int nb, int n_colblk) {
+  if (g_policy_raw == -2) g_policy_raw = env_policy("BNDM_TC_RAWL");
+  if (nb > 64) return false;                       // register budget of the 320-thread variant
+  return g_policy_raw < 0 ? n_colblk == 1 : g_policy_raw == 1;
 }
 
 }  // namespace bndm

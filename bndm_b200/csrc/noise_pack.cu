@@ -15,6 +15,8 @@ __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<floa
 
 __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
   // one thread per float4 of one packed column: 1024 float4 per column
+  pdl_launch_dependents();      // the contraction may start its set-up and L loads now
+  pdl_wait();                   // the previous call's kernels are done with zt / z_raw
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int j = (int)(idx >> 10);
   if (j >= a.n_cols_pad) return;
@@ -52,8 +54,7 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
 
 cudaError_t launch_pack(const PackArgs &a, cudaStream_t s) {
   const int64_t n4 = (int64_t)a.n_cols_pad * 1024;
-  pack_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(pack_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, a);
 }
 
 // ---- 'gaussian' 128^2 test-mode pass-through (get_noise_recent.py:50-56) ------------------
@@ -96,7 +97,9 @@ __device__ __forceinline__ void split_mode(float v, int mode, float &hi, float &
 }
 
 // one CTA per stage block: 128 rows x 32 k of L -> [Lh tile | Ll tile], SWIZZLE_128B image
-__global__ void __launch_bounds__(256) tile_L_kernel(const float *__restrict__ L, float *__restrict__ Lt, int dense, int mode) {
+// raw != 0: 16 KiB blocks holding the fp32 tile itself (converter variant of the contraction)
+__global__ void __launch_bounds__(256) tile_L_kernel(const float *__restrict__ L, float *__restrict__ Lt, int dense, int mode,
+                                                     int raw) {
   const int blk = blockIdx.x;
   int tile, s;
   if (dense) {
@@ -107,10 +110,14 @@ __global__ void __launch_bounds__(256) tile_L_kernel(const float *__restrict__ L
     while (2 * (tile + 1) * (tile + 2) <= blk) ++tile;
     s = blk - 2 * tile * (tile + 1);
   }
-  uint8_t *dst = reinterpret_cast<uint8_t *>(Lt + (size_t)blk * kLBlockFloats);
+  uint8_t *dst = reinterpret_cast<uint8_t *>(Lt + (size_t)blk * (raw ? kLBlockFloats / 2 : kLBlockFloats));
   for (int f = threadIdx.x; f < kBlk * (kStageK / 4); f += blockDim.x) {
     const int r = f >> 3, kk = (f & 7) << 2;
     const float4 v = ld4(L + (size_t)(tile * kBlk + r) * kNPix + s * kStageK + kk);
+    if (raw) {
+      *reinterpret_cast<float4 *>(dst + sw128_offset(r, kk)) = v;
+      continue;
+    }
     float4 a, b;
     split_mode(v.x, mode, a.x, b.x);
     split_mode(v.y, mode, a.y, b.y);
@@ -122,10 +129,10 @@ __global__ void __launch_bounds__(256) tile_L_kernel(const float *__restrict__ L
   }
 }
 
-cudaError_t launch_tile_L(const float *L, float *Lt, int dense, cudaStream_t s) {
+cudaError_t launch_tile_L(const float *L, float *Lt, int dense, int raw, cudaStream_t s) {
   int mode = 0;
   if (const char *e = getenv("BNDM_L_SPLIT_MODE")) mode = atoi(e);
-  tile_L_kernel<<<(unsigned)tile_L_blocks(dense), 256, 0, s>>>(L, Lt, dense, mode);
+  tile_L_kernel<<<(unsigned)tile_L_blocks(dense), 256, 0, s>>>(L, Lt, dense, mode, raw);
   return cudaGetLastError();
 }
 

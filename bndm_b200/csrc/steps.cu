@@ -13,6 +13,11 @@
 
 namespace bndm {
 
+// Resident blocks per SM the step kernels are compiled for (<= 40 registers): the cfg-2 grid of
+// 768 blocks must fit in ONE wave (measured: at 52 registers only 4 blocks fit, 1.3 waves, and
+// the half-empty second wave doubled the kernel's duration).
+constexpr int kStepBlocksPerSM = 6;
+
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
 __device__ __forceinline__ float upd1(float x, float d, float a) { return __fadd_rn(x, __fmul_rn(a, d)); }
@@ -39,37 +44,47 @@ __device__ __forceinline__ int step_from_ticket(int *state, bool &publishes) {
 // table rows: [step][sample] x {dalpha, dgamma, t_next, 0} (per-sample, like the (B,) coefficient
 // tensors the reference forms at iadb_bn.py:311-316)
 template <bool kSched, bool kVec>
-__global__ void __launch_bounds__(256) iadb_step_kernel(IadbArgs a) {
+__global__ void __launch_bounds__(256, kStepBlocksPerSM) iadb_step_kernel(IadbArgs a) {
   const bool two = a.Cd == 2 * a.C;
   constexpr int V = kVec ? 4 : 1;
   const unsigned hwv = (unsigned)(a.HW / V);
   const unsigned total = (unsigned)a.B * a.C * hwv;          // launcher guarantees < 2^31
   const unsigned first = blockIdx.x * blockDim.x + threadIdx.x;
 
-  // issue the first element's loads before touching the schedule: they do not depend on it
-  float4 xv0 = make_float4(0.f, 0.f, 0.f, 0.f), u0 = xv0, v0 = xv0;
-  if (kVec && first < total) {
-    const unsigned bc = first / hwv;
-    const int hw = (int)(first - bc * hwv) * V;
-    const int b = (int)(bc / a.C), c = (int)(bc - b * a.C);
-    const int64_t d1 = ((int64_t)b * a.Cd + c) * a.HW + hw;
-    xv0 = *reinterpret_cast<const float4 *>(a.x + (int64_t)bc * a.HW + hw);
-    u0 = ldg4(a.d + d1);
-    if (two) v0 = ldg4(a.d + d1 + (int64_t)a.C * a.HW);
-  }
+  // software pipeline: an element's loads are issued one iteration ahead -- the first ones before
+  // the ticket / schedule row (they do not depend on it), so those latencies overlap
+  const unsigned stride = gridDim.x * blockDim.x;
+  const int64_t plane = (int64_t)a.C * a.HW;
+  unsigned idx = first;
+  int b = 0;
+  int64_t xo = 0;
+  float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), u = xv, v = xv;
+  auto fetch = [&]() {
+    const unsigned bc = idx / hwv;
+    const int hw = (int)(idx - bc * hwv) * V;
+    b = (int)(bc / a.C);
+    xo = (int64_t)bc * a.HW + hw;
+    const int64_t d1 = xo + (int64_t)b * (a.Cd - a.C) * a.HW;       // ((b Cd + c) HW + hw)
+    if (kVec) {
+      xv = *reinterpret_cast<const float4 *>(a.x + xo);
+      u = ldg4(a.d + d1);
+      if (two) v = ldg4(a.d + d1 + plane);
+    } else {
+      xv.x = a.x[xo];
+      u.x = __ldg(a.d + d1);
+      if (two) v.x = __ldg(a.d + d1 + plane);
+    }
+  };
+  if (idx < total) fetch();
 
   const float4 *rows = nullptr;
-  int step = 0;
   bool publishes = false;
   if (kSched) {
-    step = step_from_ticket(a.state, publishes);
+    const int step = step_from_ticket(a.state, publishes);
     rows = reinterpret_cast<const float4 *>(a.table) + (int64_t)step * a.B;
   }
 
-  for (unsigned idx = first; idx < total; idx += gridDim.x * blockDim.x) {
-    const unsigned bc = idx / hwv;
-    const int hw = (int)(idx - bc * hwv) * V;
-    const int b = (int)(bc / a.C), c = (int)(bc - b * a.C);
+  while (idx < total) {
     float da, dg;
     if (kSched) {
       const float4 row = __ldg(rows + b);
@@ -78,40 +93,28 @@ __global__ void __launch_bounds__(256) iadb_step_kernel(IadbArgs a) {
       da = __ldg(a.dalpha + b);
       dg = two ? __ldg(a.dgamma + b) : 0.f;
     }
-    const int64_t xo = (int64_t)bc * a.HW + hw;
-    const int64_t d1 = ((int64_t)b * a.Cd + c) * a.HW + hw;
-    const int64_t d2 = d1 + (int64_t)a.C * a.HW;
-    if (kVec) {
-      float4 xv, u, v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (idx == first) {
-        xv = xv0; u = u0; v = v0;
-      } else {
-        xv = *reinterpret_cast<const float4 *>(a.x + xo);
-        u = ldg4(a.d + d1);
-        if (two) v = ldg4(a.d + d2);
-      }
-      float4 o;
-      if (two) {
-        o.x = upd2(xv.x, u.x, da, v.x, dg); o.y = upd2(xv.y, u.y, da, v.y, dg);
-        o.z = upd2(xv.z, u.z, da, v.z, dg); o.w = upd2(xv.w, u.w, da, v.w, dg);
-      } else {
-        o.x = upd1(xv.x, u.x, da); o.y = upd1(xv.y, u.y, da);
-        o.z = upd1(xv.z, u.z, da); o.w = upd1(xv.w, u.w, da);
-      }
-      *reinterpret_cast<float4 *>(a.x_out + xo) = o;
+    float4 o;
+    if (two) {
+      o.x = upd2(xv.x, u.x, da, v.x, dg);
+      if (kVec) { o.y = upd2(xv.y, u.y, da, v.y, dg); o.z = upd2(xv.z, u.z, da, v.z, dg); o.w = upd2(xv.w, u.w, da, v.w, dg); }
     } else {
-      const float xv = a.x[xo];
-      a.x_out[xo] = two ? upd2(xv, a.d[d1], da, a.d[d2], dg) : upd1(xv, a.d[d1], da);
+      o.x = upd1(xv.x, u.x, da);
+      if (kVec) { o.y = upd1(xv.y, u.y, da); o.z = upd1(xv.z, u.z, da); o.w = upd1(xv.w, u.w, da); }
     }
+    float *dst = a.x_out + xo;
+    idx += stride;
+    if (idx < total) fetch();            // next element's loads go out before this store retires
+    if (kVec) *reinterpret_cast<float4 *>(dst) = o;
+    else *dst = o.x;
   }
   if (kSched && publishes && a.t_next_out)
     for (int b = threadIdx.x; b < a.B; b += blockDim.x) a.t_next_out[b] = __ldg(rows + b).z;
 }
 
 static int grid_for(int64_t work_items, int threads) {
-  // multiple of the SM count, capped at 8 resident blocks per SM; grid-stride covers the rest
+  // at most one full wave (148 SMs x kStepBlocksPerSM resident blocks); grid-stride covers the rest
   int64_t blocks = (work_items + threads - 1) / threads;
-  const int64_t cap = 148 * 8;
+  const int64_t cap = 148 * kStepBlocksPerSM;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -143,7 +146,7 @@ __device__ __forceinline__ float ddim1(float x, float e, float z, bool has_noise
 }
 
 template <bool kVec>
-__global__ void __launch_bounds__(256) ddim_step_kernel(DdimArgs a) {
+__global__ void __launch_bounds__(256, kStepBlocksPerSM) ddim_step_kernel(DdimArgs a) {
   int step = 0;
   bool publishes = false;
   if (a.state) step = step_from_ticket(a.state, publishes);

@@ -128,6 +128,17 @@ int bndm_ddim_step_f32(float *x_out, const float *x, const float *eps, const flo
                        const float *coef, int *state, float *t_next_out, int B, int clip, int64_t n,
                        void *stream);
 
+/* Debug / test hook: force the contraction's variants (-1 = default rule, 0 = off, 1 = on):
+ * fused_combine = the last CTA of a row tile sums its partial tiles inside the contraction
+ * (default: column blocks <= 32); raw_L = raw fp32 L blocks + in-kernel lo conversion (default:
+ * one column block of <= 64 columns).  Process-wide.                                         */
+int bndm_debug_set_policy(int fused_combine, int raw_L);
+
+/* Debug: when `trace_dev` (device, 24 x u64 per CTA, >= 148 CTAs) is non-NULL the tcgen05
+ * contraction kernel records per-CTA time stamps {globaltimer in, clock in, after init, first
+ * operands landed, last MMA issued, epilogue done, clock out, globaltimer out}.               */
+int bndm_debug_set_trace(bndm_L *h, unsigned long long *trace_dev);
+
 /* Host-only consistency check of the contraction kernel's stream-K work split (no device
  * work; used by the CPU test-suite).  0 if every pipeline stage is covered exactly once and
  * the combine kernel's view of the partial tiles matches what the GEMM kernel writes.       */
