@@ -368,12 +368,15 @@ def run_ours(args):
 
 
 def get_noise_micro(torch, bb, dev, L, handle, pk):
-    """get_noise_v2 on its own at cfg 1 (B=4) and cfg 2 (B=64): whole call and per kernel,
-    L2 flushed between iterations (a 512 MB memset), next to the reference's torch op sequence
-    (get_noise_recent.py:105-116: clone, view/permute, matmul, permute/contiguous, lerp) on the
-    same GPU."""
+    """get_noise_v2 on its own at cfg 1 (B=4) and cfg 2 (B=64), whole call, L2 flushed before
+    every call (a 512 MB memset, i.e. a buffer 4x the L2 is written), next to the reference's
+    torch op sequence (get_noise_recent.py:105-116: clone, view/permute, matmul,
+    permute/contiguous, lerp) on the same GPU.  Timing: one CUDA graph of 10 x [flush, call]
+    minus one graph of 10 flushes, CUDA events around the replays -- no per-call event overhead
+    (a call is ~20 us, an event pair costs 2-4 us and is quantised to ~1 us)."""
     out = {}
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    reps = 10
 
     def torch_eager(x, gamma):
         noise = x
@@ -383,36 +386,52 @@ def get_noise_micro(torch, bb, dev, L, handle, pk):
         bn = torch.matmul(L, n).permute(0, 2, 1).contiguous().view(B, C, RES, RES)
         return bn * (1 - gamma.view(-1, 1, 1, 1)) + wn * gamma.view(-1, 1, 1, 1), bn, wn
 
+    def graph_us(fn):
+        def capture(body):
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                body()                                  # lazy initialisation outside capture
+            torch.cuda.current_stream(dev).wait_stream(side)
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(reps):
+                    flush.zero_()
+                    body()
+            return g
+        res = []
+        for body in (fn, lambda: None):
+            g = capture(body)
+            g.replay()
+            torch.cuda.synchronize(dev)
+            ts = []
+            for _ in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                g.replay()
+                e1.record()
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1) * 1e3 / reps)
+            res.append(statistics.median(ts))
+        return res[0] - res[1]
+
+    was_profiling = handle.profile_enabled
+    handle.profile(False)                               # no events between the PDL-chained kernels
     for B in (4, 64):
         x = torch.randn(B, CH, RES, RES, device=dev)
         gamma = torch.rand(B, device=dev)
         n_cols = B * CH
+        handle.reserve(n_cols)
         res = {}
         for name, n_out, fn in (("ours_3_outputs", 3, lambda: bb.get_noise_v2(dev, x, handle, gamma, None, "gaussianBN", "train", True)),
                                 ("ours_1_output", 1, lambda: bb.get_noise_v2(dev, x, handle, gamma, None, "gaussianBN", "train", True, want=("noise",))),
                                 ("torch_eager_reference_ops", 3, lambda: torch_eager(x, gamma))):
-            for cold in (True, False):
-                times, parts = [], []
-                for it in range(13):
-                    if cold:
-                        flush.zero_()
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                    fn()
-                    e1.record()
-                    e1.synchronize()
-                    if it >= 3:
-                        times.append(e0.elapsed_time(e1))
-                        if name.startswith("ours"):
-                            parts.append(handle.last_ms())
-                ms = statistics.median(times)
-                alg = L_TRI_BYTES + 4 * 4096 * n_cols * (1 + n_out)
-                r = {"ms": ms, "algorithmic_bytes": alg, "gbs": alg / (ms * 1e-3) / 1e9,
-                     "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
-                if parts:
-                    r["pack_ms"], r["gemm_ms"], r["epilogue_ms"] = (statistics.median(p[i] for p in parts) for i in range(3))
-                res[name + ("_l2_cold" if cold else "_l2_warm")] = r
+            us = graph_us(fn)
+            alg = L_TRI_BYTES + 4 * 4096 * n_cols * (1 + n_out)
+            res[name + "_l2_cold"] = {"us": us, "algorithmic_bytes": alg, "gbs": alg / us / 1e3,
+                                      "frac_of_hbm_peak": alg / us / 1e3 / pk["hbm_gbs"]}
         out[f"B{B}_C{CH}_res{RES}"] = res
+    handle.profile(was_profiling)
     return out
 
 

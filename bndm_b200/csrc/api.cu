@@ -281,7 +281,10 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
   const int n_cols_pad = (n_cols + nb - 1) / nb * nb;
   const int n_row_tiles = mode == kRes32 ? kNumBlk / 2 : kNumBlk;
   const Schedule sched = pick_schedule(n_row_tiles, dense, (n_cols_pad + 63) / 64);          // SIMT path
-  const StreamK sk = make_streamk(n_row_tiles, dense, n_cols_pad / nb, tc_num_sms());         // tcgen05 path
+  // raw-operand variant of the contraction: takes fp32 columns as they are (caller's tensor or the
+  // gathered z_raw) and converts in shared memory -> the pack kernel only runs to gather
+  const bool raw = !simt && !dense && h->Lr && tc_raw_L(nb, n_cols_pad / nb) && (reinterpret_cast<uintptr_t>(z) % 16 == 0);
+  const StreamK sk = make_streamk(n_row_tiles, dense, n_cols_pad / nb, tc_num_sms(), tc_sub(nb, raw));   // tcgen05 path
   const size_t need = simt ? (size_t)sched.n_units() * n_cols_pad * kBlk : (size_t)sk.n_slots() * nb * kBlk;
   if (n_cols_pad > h->cap_cols || need > h->cap_partial) {
     int rc = bndm_reserve_columns(h, n_cols > h->req_cols ? n_cols : h->req_cols + 1, stream);
@@ -299,7 +302,7 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
   PackArgs p;
   p.src = z;
   p.z_raw = need_raw ? h->z_raw : nullptr;
-  p.zt = simt ? nullptr : h->zt;
+  p.zt = (simt || raw) ? nullptr : h->zt;
   p.nb = nb;
   p.n_cols = n_cols;
   p.n_cols_pad = n_cols_pad;
@@ -309,7 +312,7 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
   p.src_is_image = src_is_image;
   const bool prof = h->profile && !stream_is_capturing(s);
   if (prof) CK(cudaEventRecord(h->ev[0], s));
-  CK(launch_pack(p, s));
+  if (p.z_raw || p.zt) CK(launch_pack(p, s));
   if (prof) CK(cudaEventRecord(h->ev[1], s));
   const float *z_cols = need_raw ? h->z_raw : z;
 
@@ -342,7 +345,7 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
     TcGemmArgs g;
     g.Lt = h->Lt;
     g.raw_L = 0;
-    if (!dense && h->Lr && tc_raw_L(nb, sk.n_colblk)) {
+    if (raw) {
       g.Lt = h->Lr;
       g.raw_L = 1;
     }
@@ -454,7 +457,12 @@ int bndm_ddim_step_f32(float *x_out, const float *x, const float *eps, const flo
 // covered exactly once, segment slots are unique and below n_slots(), and the slot range the
 // combine kernel derives for a row tile is exactly the set of segments the GEMM writes for it.
 int bndm_debug_streamk_check(int n_tiles, int dense, int n_colblk, int num_sms) {
-  const StreamK k = make_streamk(n_tiles, dense, n_colblk, num_sms);
+  return bndm_debug_streamk_check_sub(n_tiles, dense, n_colblk, num_sms, 1);
+}
+
+int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_sms, int sub) {
+  if (sub != 1 && sub != 2) { set_error("streamk: sub must be 1 or 2"); return BNDM_ERR_ARG; }
+  const StreamK k = make_streamk(n_tiles, dense, n_colblk, num_sms, sub);
   if (k.G < 1 || k.G > num_sms || k.W != n_colblk * k.Stot) { set_error("streamk: bad G/W"); return BNDM_ERR_ARG; }
   const int ns = k.n_slots();
   int *owner = new int[ns];
@@ -497,6 +505,26 @@ int bndm_debug_streamk_check(int n_tiles, int dense, int n_colblk, int num_sms) 
   delete[] owner;
   delete[] tile_of;
   return rc;
+}
+
+int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_bc, const float *weight, const float *bias,
+                            float *sum_out, float *y, int B, int C, int HW, int groups, float eps, int apply_silu,
+                            void *stream) {
+  if (!x || !weight || !bias || !y || B < 1 || C < 1 || HW < 1 || groups < 1) { set_error("groupnorm: bad argument"); return BNDM_ERR_ARG; }
+  if (C % groups != 0 || (C / groups) % 4 != 0) {
+    set_error("groupnorm: channels per group must be a multiple of 4 (C=%d, groups=%d)", C, groups);
+    return BNDM_ERR_UNSUPPORTED;
+  }
+  uintptr_t al = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(weight) |
+                 reinterpret_cast<uintptr_t>(bias);
+  if (res) al |= reinterpret_cast<uintptr_t>(res);
+  if (add_bc) al |= reinterpret_cast<uintptr_t>(add_bc);
+  if (sum_out) al |= reinterpret_cast<uintptr_t>(sum_out);
+  if (al % 16 != 0) { set_error("groupnorm: pointers must be 16-byte aligned"); return BNDM_ERR_ARG; }
+  cudaError_t e = launch_groupnorm_nhwc(x, res, add_bc, weight, bias, sum_out, y, B, C, HW, groups, eps, apply_silu, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) { set_error("groupnorm: unsupported shape C=%d groups=%d", C, groups); return BNDM_ERR_UNSUPPORTED; }
+  CK(e);
+  return BNDM_OK;
 }
 
 int bndm_to_uint8_nhwc(const float *x, uint8_t *out, int B, int C, int H, int W, void *stream) {

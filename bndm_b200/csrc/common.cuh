@@ -129,10 +129,11 @@ struct StreamK {
   int dense;      // 0: lower-triangular, 1: dense
   int n_colblk;   // column blocks of nb columns
   int G;          // CTAs = min(#SMs, W)
-  int Stot;       // stages per column block
+  int Stot;       // units per column block
   int W;          // n_colblk * Stot
-  // stages of row tiles [0, i): also the index of tile i's first stage block in Lt
-  __host__ __device__ int cum(int i) const { return dense ? (kNPix / kStageK) * i : 2 * i * (i + 1); }
+  int sub;        // k-stages (32 k each) per schedule unit / pipeline stage: 1 or 2
+  // units of row tiles [0, i); times `sub` = index of tile i's first stage block in Lt
+  __host__ __device__ int cum(int i) const { return (dense ? (kNPix / kStageK) * i : 2 * i * (i + 1)) / sub; }
   __host__ __device__ int cta_begin(int c) const { return (int)((int64_t)c * W / G); }
   __host__ __device__ int cta_of(int g) const { return (int)((((int64_t)g + 1) * G - 1) / W); }
   __host__ __device__ int tile_begin(int cb, int tile) const { return cb * Stot + Stot - cum(tile + 1); }
@@ -154,8 +155,9 @@ struct StreamK {
   __host__ __device__ int first_cta(int cb, int tile) const { return cta_of(tile_begin(cb, tile)); }
   __host__ __device__ int last_cta(int cb, int tile) const { return cta_of(tile_end(cb, tile) - 1); }
 };
-inline StreamK make_streamk(int n_tiles, int dense, int n_colblk, int num_sms) {
+inline StreamK make_streamk(int n_tiles, int dense, int n_colblk, int num_sms, int sub = 1) {
   StreamK k;
+  k.sub = sub;
   k.n_tiles = n_tiles;
   k.dense = dense;
   k.n_colblk = n_colblk;
@@ -187,6 +189,7 @@ int tc_pick_nb(int n_cols);   // column block for a given column count
 int tc_num_sms();
 bool tc_fused_combine(int nb);
 bool tc_raw_L(int nb, int n_colblk);   // policy: raw-L converter variant for this shape?
+int tc_sub(int nb, bool raw);          // policy: k-stages per pipeline stage (2 = 32 KiB L requests)
 void tc_set_policy(int fused, int raw);   // policy: combine fused into the contraction for this column block?
 
 // combine of the stream-K partials + everything get_noise_v2 does after the matmul
@@ -225,6 +228,9 @@ struct DdimArgs {
 };
 
 cudaError_t launch_ddim_step(const DdimArgs &a, cudaStream_t s);
+cudaError_t launch_groupnorm_nhwc(const float *x, const float *res, const float *add_bc, const float *weight,
+                                  const float *bias, float *sum_out, float *y, int B, int C, int HW, int groups, float eps,
+                                  int silu, cudaStream_t s);
 cudaError_t launch_to_u8(const float *x, uint8_t *out, int B, int C, int HW, cudaStream_t s);
 
 // ---- tf32 split (round-to-nearest-away hi, residual lo) -----------------------------------

@@ -34,7 +34,9 @@
 // CTA = 6 warps: warp 0 = producer (1 lane issues the bulk copies), warp 1 = TMEM alloc + MMA
 // issuer (1 lane), warps 2..5 = epilogue.  Pipelines: smem stage ring (producer <-> issuer),
 // two TMEM accumulator buffers (issuer <-> epilogue), the static stream-K schedule.
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "out_map.cuh"
@@ -80,6 +82,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (++spins > kSpinLimit) __trap();
   }
 }
+// one lane of a converged warp (warp-uniform control flow around it keeps descriptors and
+// addresses in uniform registers: no per-instruction R2UR traffic in the issue loops)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // linear global -> shared bulk copy (TMA engine), completion counted in bytes on `bar`
@@ -87,6 +100,15 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
   asm volatile(
       "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+
+// 2-D tiled TMA load (tensor map), 128-byte swizzle applied by the hardware, OOB rows zero-filled
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
       : "memory");
 }
 
@@ -197,14 +219,34 @@ struct ChainWalk {
 // raw tile IS the hi operand, and four converter warps (6..9) write  Ll = L - trunc_tf32(L)
 // (exact in fp32) next to it in shared memory before the issuer may read the stage.  Halves the
 // bytes streamed from HBM; used when one column block covers the call (HBM-bound regime).
-template <int NB, bool kRawL>
-__global__ void __launch_bounds__(kRawL ? kThreadsRaw : kThreads, 1) gemm_tc_kernel(const TcKernelArgs a) {
-  constexpr uint32_t kLBlockBytes = 2 * kBlk * kStageK * 4;       // 32 KiB in smem: Lh tile | Ll tile
-  constexpr uint32_t kLLoadBytes = kRawL ? kLBlockBytes / 2 : kLBlockBytes;     // bytes per stage from HBM
+// The raw variant also takes z as the caller's fp32 columns [n_cols][4096] through a 2-D tensor
+// map (hardware swizzle, rows past n_cols zero-filled) and converts it the same way, so a call
+// whose white field is already in column order runs NO pack kernel.  Its accumulators are laid
+// out as kSets x [main | Lh.zl | Ll.zh]: consecutive MMAs never target the same TMEM columns
+// (back-to-back MMAs into one accumulator serialise on the tensor pipe's latency when N is small).
+// kSub = 2: a pipeline stage holds TWO consecutive k-stages (64 k): their raw L tiles are adjacent
+// in HBM and come in with one 32 KiB bulk copy -- at 16 KiB per request the memory system
+// delivered ~4 TB/s to this kernel, at 32 KiB ~7 (measured) -- and barrier round trips, the
+// converter's fence and the commit are paid once per 64 k.  Shared-memory image of a stage:
+//   [ L hi/raw x kSub | L lo x kSub | (z hi/raw | z lo) x kSub ]
+template <int NB, bool kRawL, int kSub>
+__global__ void __launch_bounds__(kRawL ? kThreadsRaw : kThreads, 1)
+gemm_tc_kernel(const TcKernelArgs a, const __grid_constant__ CUtensorMap map_z) {
+  constexpr uint32_t kTileBytes = kBlk * kStageK * 4;             // 16 KiB: one 128 x 32 fp32 operand tile
+  constexpr uint32_t kLBlockBytes = 2 * kTileBytes;               // hi + lo tile of one k-stage in smem
+  constexpr uint32_t kLLoadBytes = kRawL ? kTileBytes : kLBlockBytes;           // bytes per k-stage from HBM
   constexpr uint32_t kZBlockBytes = 2 * NB * kStageK * 4;         // zh rows | zl rows
-  constexpr uint32_t kStageBytes = kLBlockBytes + kZBlockBytes;
-  constexpr uint32_t kBufCols = 2 * NB;                           // main | correction
-  constexpr uint32_t kTmemCols = 4 * NB <= 32 ? 32 : 4 * NB <= 64 ? 64 : 4 * NB <= 128 ? 128 : 4 * NB <= 256 ? 256 : 512;
+  constexpr uint32_t kZLoadBytes = kRawL ? kZBlockBytes / 2 : kZBlockBytes;
+  constexpr uint32_t kStageBytes = kSub * (kLBlockBytes + kZBlockBytes);
+  constexpr uint32_t kLoOff = kSub * kTileBytes;                  // lo tiles start here
+  constexpr uint32_t kZOff = kSub * kLBlockBytes;                 // z blocks start here
+  static_assert(kSub == 1 || kRawL, "two k-stages per pipeline stage only in the raw-operand variant");
+  constexpr int kSets = kRawL ? (NB <= 32 ? 2 : 1) : 1;           // independent accumulator sets (alternate per 8 k)
+  constexpr uint32_t kSetCols = kRawL ? 3 * NB : 2 * NB;          // raw: main | c1 | c2;  pre-split: main | c1+c2
+  constexpr uint32_t kBufCols = kSets * kSetCols;
+  constexpr uint32_t kTmemNeed = 2 * kBufCols;
+  constexpr uint32_t kTmemCols = kTmemNeed <= 32 ? 32 : kTmemNeed <= 64 ? 64 : kTmemNeed <= 128 ? 128 : kTmemNeed <= 256 ? 256 : 512;
+  static_assert(kTmemNeed <= 512, "accumulators do not fit in TMEM");
   static_assert(NB % 16 == 0 && NB >= 16 && NB <= 128, "column block must be a multiple of 16 in [16, 128]");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -230,6 +272,7 @@ __global__ void __launch_bounds__(kRawL ? kThreadsRaw : kThreads, 1) gemm_tc_ker
     for (int i = (lane - 1) * 32; i < a.om.B; i += 31 * 32)
       asm volatile("prefetch.global.L2 [%0];" ::"l"(a.om.gamma + i));
   }
+  if (kRawL && warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_z) : "memory");
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -242,51 +285,75 @@ __global__ void __launch_bounds__(kRawL ? kThreadsRaw : kThreads, 1) gemm_tc_ker
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // Set-up barrier (named barrier 2): the producer warp only ARRIVES -- its first loads go out
+  // while warp 1 is still allocating TMEM (it never needs the TMEM address); everyone else waits.
+  constexpr int kAllThreads = kRawL ? kThreadsRaw : kThreads;
+  uint32_t tmem_base = 0;
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("bar.arrive 2, %0;" ::"n"(kAllThreads) : "memory");
+  } else {
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+    asm volatile("bar.sync 2, %0;" ::"n"(kAllThreads) : "memory");
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+  }
   if (tr && threadIdx.x == 0) tr[2] = clock64();
 
   if (warp == 0) {
     // ================= producer: one bulk copy per operand per stage =================
-    if (lane == 0) {
+    {
       // L is never written by a preceding kernel: its loads go out at once; the z blocks are
       // the pack kernel's output, so the first of them waits for that grid (PDL)
       bool z_ready = false;
       ChainWalk w(a.sk, cta, a.chain);
       int it = 0;
       while (w.next()) {
-        const float *Lblk = a.Lt + (size_t)(a.sk.cum(w.tile) + w.s0) * (kLLoadBytes / 4);
-        const float *zblk = a.zt + (size_t)(w.cb * (kNPix / kStageK) + w.s0) * (kZBlockBytes / 4);
+        // w.s0 / w.n count schedule units of kSub k-stages
+        const float *Lblk = a.Lt + (size_t)(a.sk.cum(w.tile) + w.s0) * kSub * (kLLoadBytes / 4);
+        const float *zblk = a.zt + (size_t)(w.cb * (kNPix / kStageK) + w.s0 * kSub) * (kZBlockBytes / 4);
         for (int n = 0; n < w.n; ++n, ++it) {
           const int st = it % a.stages;
           const uint32_t ph = (uint32_t)(it / a.stages) & 1u;
           const long long t0 = tr ? clock64() : 0;
           mbar_wait(&empty_bar[st], ph ^ 1u);
-          if (tr) tr[20] += (unsigned long long)(clock64() - t0);
+          if (tr && lane == 0) tr[20] += (unsigned long long)(clock64() - t0);
           const uint32_t sa = smem_u32(base + (size_t)st * kStageBytes);
-          mbar_expect_tx(&full_bar[st], kLLoadBytes + kZBlockBytes);
-          bulk_load(sa, Lblk + (size_t)n * (kLLoadBytes / 4), kLLoadBytes, &full_bar[st], a.policy_L);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[st], kSub * (kLLoadBytes + kZLoadBytes));
+            bulk_load(sa, Lblk + (size_t)n * kSub * (kLLoadBytes / 4), kSub * kLLoadBytes, &full_bar[st], a.policy_L);
+          }
           if (!z_ready) {
             pdl_wait();
             z_ready = true;
           }
-          bulk_load(sa + kLBlockBytes, zblk + (size_t)n * (kZBlockBytes / 4), kZBlockBytes, &full_bar[st], kEvictLast);
+          if (elect_one()) {
+            if (kRawL) {
+#pragma unroll
+              for (int sb = 0; sb < kSub; ++sb)
+                tma_load_2d(sa + kZOff + sb * kZBlockBytes, &map_z, &full_bar[st], ((w.s0 + n) * kSub + sb) * kStageK, w.cb * NB,
+                            kEvictLast);
+            } else {
+              bulk_load(sa + kZOff, zblk + (size_t)n * (kZBlockBytes / 4), kZBlockBytes, &full_bar[st], kEvictLast);
+            }
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_wide = umma_idesc(2 * NB), idesc_narrow = umma_idesc(NB);
       ChainWalk w(a.sk, cta, a.chain);
       int it = 0, ch = 0;
       for (; w.next(); ++ch) {
         const int buf = ch & 1;
+        const long long ta = tr ? clock64() : 0;
         mbar_wait(&acc_empty[buf], (((uint32_t)ch >> 1) & 1u) ^ 1u);      // epilogue drained this buffer
         tc_fence_after();
+        if (tr && lane == 0) tr[19] += (unsigned long long)(clock64() - ta);
         const uint32_t tmem_d = tmem_base + (uint32_t)buf * kBufCols;
         for (int n = 0; n < w.n; ++n, ++it) {
           const int st = it % a.stages;
@@ -294,23 +361,38 @@ __global__ void __launch_bounds__(kRawL ? kThreadsRaw : kThreads, 1) gemm_tc_ker
           const long long t0 = tr ? clock64() : 0;
           mbar_wait(kRawL ? &conv_bar[st] : &full_bar[st], ph);
           tc_fence_after();
-          if (tr) tr[18] += (unsigned long long)(clock64() - t0);
-          if (tr && it == 0) tr[3] = clock64();
+          if (tr && lane == 0) tr[18] += (unsigned long long)(clock64() - t0);
+          if (tr && it == 0 && lane == 0) tr[3] = clock64();
           const uint32_t sa = smem_u32(base + (size_t)st * kStageBytes);
-          const uint64_t dAh = umma_desc(sa);
-          const uint64_t dAl = umma_desc(sa + kLBlockBytes / 2);
-          const uint64_t dB = umma_desc(sa + kLBlockBytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < kStageK / kUmmaK; ++kk) {
-            const uint64_t adv = (uint64_t)((kk * kUmmaK * 4) >> 4);   // +32 B inside the swizzle row
-            umma_tf32(tmem_d, dAh + adv, dB + adv, idesc_wide, (n | kk) != 0);      // Lh x [zh | zl]
-            umma_tf32(tmem_d + NB, dAl + adv, dB + adv, idesc_narrow, 1u);          // Ll x zh
+          for (int sb = 0; sb < kSub; ++sb) {
+            const uint64_t dAh = umma_desc(sa + sb * kTileBytes);
+            const uint64_t dAl = umma_desc(sa + kLoOff + sb * kTileBytes);
+            const uint64_t dB = umma_desc(sa + kZOff + sb * kZBlockBytes);
+#pragma unroll
+            for (int kk = 0; kk < kStageK / kUmmaK; ++kk) {
+              const uint64_t adv = (uint64_t)((kk * kUmmaK * 4) >> 4);   // +32 B inside the swizzle row
+              if (kRawL) {
+                const uint32_t d = tmem_d + (uint32_t)(kk % kSets) * kSetCols;
+                const uint32_t fresh = (n == 0 && sb == 0 && kk < kSets) ? 0u : 1u;    // first MMA into this set
+                umma_tf32(d, dAh + adv, dB + adv, idesc_wide, fresh);                  // Lh x [zh | zl] -> main | c1
+                umma_tf32(d + 2 * NB, dAl + adv, dB + adv, idesc_narrow, fresh);       // Ll x zh        -> c2
+              } else {
+                umma_tf32(tmem_d, dAh + adv, dB + adv, idesc_wide, (n | kk) != 0);     // Lh x [zh | zl]
+                umma_tf32(tmem_d + NB, dAl + adv, dB + adv, idesc_narrow, 1u);         // Ll x zh
+              }
+            }
           }
           umma_commit(&empty_bar[st]);       // frees the smem stage when these MMAs retire
+          }
+          __syncwarp();
+          if (tr && lane == 0) tr[21] += (unsigned long long)(clock64() - t0);
         }
-        umma_commit(&acc_full[buf]);         // this chain's accumulators are complete
+        if (elect_one()) umma_commit(&acc_full[buf]);         // this chain's accumulators are complete
+        __syncwarp();
       }
-      if (tr) tr[4] = clock64();
+      if (tr && lane == 0) tr[4] = clock64();
     }
   } else if (kRawL && warp >= 6) {
     // ================= converter: Ll = L - trunc_tf32(L), 8 x 16 bytes per thread per stage =================
@@ -325,18 +407,36 @@ __global__ void __launch_bounds__(kRawL ? kThreadsRaw : kThreads, 1) gemm_tc_ker
         mbar_wait(&full_bar[st], ph);
         const long long t1 = (tr && t == 0) ? clock64() : 0;
         const float4 *src = reinterpret_cast<const float4 *>(base + (size_t)st * kStageBytes) + t;
-        float4 *dst = reinterpret_cast<float4 *>(base + (size_t)st * kStageBytes + kLBlockBytes / 2) + t;
-        float4 v[8];
+        float4 *dst = reinterpret_cast<float4 *>(base + (size_t)st * kStageBytes + kLoOff) + t;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = src[i * 128];
+        for (int half = 0; half < kSub; ++half) {
+          float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 lo;
-          lo.x = __fsub_rn(v[i].x, __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u));
-          lo.y = __fsub_rn(v[i].y, __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u));
-          lo.z = __fsub_rn(v[i].z, __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u));
-          lo.w = __fsub_rn(v[i].w, __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u));
-          dst[i * 128] = lo;
+          for (int i = 0; i < 8; ++i) v[i] = src[(half * 8 + i) * 128];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 lo;
+            lo.x = __fsub_rn(v[i].x, __uint_as_float(__float_as_uint(v[i].x) & 0xFFFFE000u));
+            lo.y = __fsub_rn(v[i].y, __uint_as_float(__float_as_uint(v[i].y) & 0xFFFFE000u));
+            lo.z = __fsub_rn(v[i].z, __uint_as_float(__float_as_uint(v[i].z) & 0xFFFFE000u));
+            lo.w = __fsub_rn(v[i].w, __uint_as_float(__float_as_uint(v[i].w) & 0xFFFFE000u));
+            dst[(half * 8 + i) * 128] = lo;
+          }
+        }
+#pragma unroll
+        for (int sb = 0; sb < kSub; ++sb) {  // zl = z - trunc_tf32(z): NB rows x 128 B per k-stage
+          const float4 *zs = reinterpret_cast<const float4 *>(base + (size_t)st * kStageBytes + kZOff + sb * kZBlockBytes);
+          float4 *zd = reinterpret_cast<float4 *>(base + (size_t)st * kStageBytes + kZOff + sb * kZBlockBytes + kZBlockBytes / 2);
+#pragma unroll
+          for (int i = t; i < NB * 8; i += 128) {
+            const float4 z4 = zs[i];
+            float4 lo;
+            lo.x = __fsub_rn(z4.x, __uint_as_float(__float_as_uint(z4.x) & 0xFFFFE000u));
+            lo.y = __fsub_rn(z4.y, __uint_as_float(__float_as_uint(z4.y) & 0xFFFFE000u));
+            lo.z = __fsub_rn(z4.z, __uint_as_float(__float_as_uint(z4.z) & 0xFFFFE000u));
+            lo.w = __fsub_rn(z4.w, __uint_as_float(__float_as_uint(z4.w) & 0xFFFFE000u));
+            zd[i] = lo;
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core
         __syncwarp();
@@ -360,15 +460,34 @@ __global__ void __launch_bounds__(kRawL ? kThreadsRaw : kThreads, 1) gemm_tc_ker
       mbar_wait(&acc_full[buf], ((uint32_t)ch >> 1) & 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * kBufCols;
+      if (kRawL) {
+        // a chain shorter than kSets MMAs per stage cannot happen (4 MMAs per stage, kSets <= 2)
 #pragma unroll
-      for (int c = 0; c < NB; c += 16) {
-        uint32_t m[16], x[16];
-        tmem_ld16(taddr + (uint32_t)c, m);
-        tmem_ld16(taddr + (uint32_t)(NB + c), x);
-        tmem_ld_wait();
+        for (int set = 0; set < kSets; ++set)
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          acc[c + e] = __fadd_rn(acc[c + e], __fadd_rn(__uint_as_float(m[e]), __uint_as_float(x[e])));
+          for (int c = 0; c < NB; c += 16) {
+            uint32_t m[16], x[16], y[16];
+            const uint32_t t0 = taddr + (uint32_t)set * kSetCols + (uint32_t)c;
+            tmem_ld16(t0, m);
+            tmem_ld16(t0 + NB, x);
+            tmem_ld16(t0 + 2 * NB, y);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+              acc[c + e] = __fadd_rn(acc[c + e], __fadd_rn(__uint_as_float(m[e]),
+                                                            __fadd_rn(__uint_as_float(x[e]), __uint_as_float(y[e]))));
+          }
+      } else {
+#pragma unroll
+        for (int c = 0; c < NB; c += 16) {
+          uint32_t m[16], x[16];
+          tmem_ld16(taddr + (uint32_t)c, m);
+          tmem_ld16(taddr + (uint32_t)(NB + c), x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            acc[c + e] = __fadd_rn(acc[c + e], __fadd_rn(__uint_as_float(m[e]), __uint_as_float(x[e])));
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -514,14 +633,42 @@ static int tc_chain() {
   return v;
 }
 
-template <int NB, bool kRawL>
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// fp32 columns [rows][4096] row-major, box = [box_rows][32 k], 128-byte swizzle, OOB rows read as zero
+static bool make_z_map(CUtensorMap *m, const float *ptr, int rows, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)kNPix, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kNPix * 4};
+  cuuint32_t box[2] = {(cuuint32_t)kStageK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NB, bool kRawL, int kSub>
 static cudaError_t launch_nb(const TcGemmArgs &g, cudaStream_t s) {
   TcKernelArgs a;
   a.Lt = g.Lt;
   a.zt = g.zt;
   a.partials = g.partials;
   a.sk = g.sk;
-  a.chain = tc_chain();
+  a.chain = tc_chain() / kSub > 0 ? tc_chain() / kSub : 1;       // schedule units per TMEM chain
   a.trace = g.trace;
   a.tile_counters = g.tile_counters;
   a.om = OutMap{g.z_cols, g.gamma, g.out, g.out_bn, g.out_wn, g.B, g.C, g.res_mode};
@@ -529,7 +676,7 @@ static cudaError_t launch_nb(const TcGemmArgs &g, cudaStream_t s) {
   // L is streamed once per call when there is one column block; with several, the CTAs of the
   // other column blocks read the same stage blocks at about the same time -> keep them in L2
   a.policy_L = g.sk.n_colblk == 1 ? kEvictFirst : kEvictNormal;
-  const uint32_t stage_bytes = 2 * kBlk * kStageK * 4 + 2 * NB * kStageK * 4;
+  const uint32_t stage_bytes = kSub * (2 * kBlk * kStageK * 4 + 2 * NB * kStageK * 4);
   const uint32_t budget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
   // One column block (cold L2): the kernel is HBM-bound and more than ~100 KiB in flight per SM
   // only lengthens the DRAM queue, i.e. spreads the time the first operands land and with it
@@ -537,7 +684,7 @@ static cudaError_t launch_nb(const TcGemmArgs &g, cudaStream_t s) {
   // shared-memory bandwidth bounds a stage -> as deep as fits.
   int stages = (int)(budget / stage_bytes);
   if (stages > 8) stages = 8;
-  if (g.sk.n_colblk == 1 && stages > (kRawL ? 5 : 3)) stages = kRawL ? 5 : 3;
+  if (g.sk.n_colblk == 1 && stages > (kRawL && kSub == 1 ? 5 : 3)) stages = kRawL && kSub == 1 ? 5 : 3;
   if (const char *e = getenv("BNDM_TC_STAGES")) {     // experiment knob: shallower ring
     const int x = atoi(e);
     const int fit = (int)(budget / stage_bytes) < 8 ? (int)(budget / stage_bytes) : 8;
@@ -545,34 +692,59 @@ static cudaError_t launch_nb(const TcGemmArgs &g, cudaStream_t s) {
   }
   a.stages = stages;
   const size_t smem = (size_t)stages * stage_bytes + 1024 + (3 * stages + 4) * 8 + 16;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NB, kRawL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<NB, kRawL, kSub>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024));
   if (e != cudaSuccess) return e;
-  return launch_pdl(gemm_tc_kernel<NB, kRawL>, dim3(g.sk.G), dim3(kRawL ? kThreadsRaw : kThreads), smem, s, a);
+  CUtensorMap map_z;
+  memset(&map_z, 0, sizeof(map_z));
+  if (kRawL && !make_z_map(&map_z, g.z_cols, g.n_cols, NB)) {
+    set_error("cuTensorMapEncodeTiled failed (columns %d, block %d)", g.n_cols, NB);
+    return cudaErrorInvalidValue;
+  }
+  return launch_pdl(gemm_tc_kernel<NB, kRawL, kSub>, dim3(g.sk.G), dim3(kRawL ? kThreadsRaw : kThreads), smem, s, a, map_z);
 }
 
 cudaError_t launch_gemm_tc(const TcGemmArgs &g, cudaStream_t s) {
   if (g.raw_L) {
+    if (g.sk.sub == 2) {
+      switch (g.nb) {
+        case 16: return launch_nb<16, true, 2>(g, s);
+        case 32: return launch_nb<32, true, 2>(g, s);
+      }
+      set_error("tcgen05 contraction (raw L, 64-k stages): unsupported column block %d", g.nb);
+      return cudaErrorInvalidValue;
+    }
     switch (g.nb) {
-      case 16: return launch_nb<16, true>(g, s);
-      case 32: return launch_nb<32, true>(g, s);
-      case 48: return launch_nb<48, true>(g, s);
-      case 64: return launch_nb<64, true>(g, s);
+      case 16: return launch_nb<16, true, 1>(g, s);
+      case 32: return launch_nb<32, true, 1>(g, s);
+      case 48: return launch_nb<48, true, 1>(g, s);
+      case 64: return launch_nb<64, true, 1>(g, s);
     }
     set_error("tcgen05 contraction (raw L): unsupported column block %d", g.nb);
     return cudaErrorInvalidValue;
   }
   switch (g.nb) {
-    case 16: return launch_nb<16, false>(g, s);
-    case 32: return launch_nb<32, false>(g, s);
-    case 48: return launch_nb<48, false>(g, s);
-    case 64: return launch_nb<64, false>(g, s);
-    case 80: return launch_nb<80, false>(g, s);
-    case 96: return launch_nb<96, false>(g, s);
-    case 112: return launch_nb<112, false>(g, s);
-    case 128: return launch_nb<128, false>(g, s);
+    case 16: return launch_nb<16, false, 1>(g, s);
+    case 32: return launch_nb<32, false, 1>(g, s);
+    case 48: return launch_nb<48, false, 1>(g, s);
+    case 64: return launch_nb<64, false, 1>(g, s);
+    case 80: return launch_nb<80, false, 1>(g, s);
+    case 96: return launch_nb<96, false, 1>(g, s);
+    case 112: return launch_nb<112, false, 1>(g, s);
+    case 128: return launch_nb<128, false, 1>(g, s);
   }
   set_error("tcgen05 contraction: unsupported column block %d", g.nb);
   return cudaErrorInvalidValue;
+}
+
+int tc_sub(int nb, bool raw) {
+  static int v = -2;           // BNDM_TC_SUB=1/2 forces it (experiments)
+  if (v == -2) {
+    const char *e = getenv("BNDM_TC_SUB");
+    v = e ? atoi(e) : -1;
+  }
+  if (!raw || nb > 32) return 1;
+  if (v == 1 || v == 2) return v;
+  return nb == 16 ? 2 : 1;     // 3 stages of 2 x (32 KiB + z) must fit in shared memory
 }
 
 bool tc_raw_L(int nb, int n_colblk) {

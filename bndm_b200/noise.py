@@ -37,6 +37,7 @@ class CovMatL:
                                     _lib.current_stream(self.device), _lib.C.byref(handle))
         _lib.check(rc, "bndm_prepare_L")
         self._h = handle
+        self.profile_enabled = False
         self._finalizer = weakref.finalize(self, lib.bndm_free_L, handle)
 
     @property
@@ -55,6 +56,7 @@ class CovMatL:
 
     def profile(self, on=True):
         _lib.check(_lib.load().bndm_profile_enable(self._h, 1 if on else 0), "bndm_profile_enable")
+        self.profile_enabled = bool(on)
 
     def last_ms(self):
         """(pack, contraction, epilogue) milliseconds of the last profiled get_noise call."""

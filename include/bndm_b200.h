@@ -143,6 +143,20 @@ int bndm_debug_set_trace(bndm_L *h, unsigned long long *trace_dev);
  * work; used by the CPU test-suite).  0 if every pipeline stage is covered exactly once and
  * the combine kernel's view of the partial tiles matches what the GEMM kernel writes.       */
 int bndm_debug_streamk_check(int n_tiles, int dense, int n_colblk, int num_sms);
+/* Same with `sub` k-stages per schedule unit (1, or 2 = the 64-k pipeline stages of the raw-operand
+ * variant).                                                                                    */
+int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_sms, int sub);
+
+/* K5 -- the UNet's normalisation glue on channels-last activations (diffusers ResnetBlock2D
+ * norm/act sequence of the model built at iadb_bn.py:205-282 and called at :319), one kernel:
+ *     s = x (+ res) (+ add_bc[b][c]);  sum_out = s (if non-NULL)
+ *     y = act((s - mean_group) * rstd_group * weight[c] + bias[c]),  act = SiLU iff apply_silu
+ * x, res, sum_out, y: dev, NHWC [B][HW][C] fp32; add_bc: dev [B][C] or NULL; weight, bias: dev [C].
+ * groups as torch.nn.GroupNorm (biased variance, eps inside the sqrt); C/groups % 4 == 0.
+ * Replaces RowwiseMoments + affine + SiLU (+ broadcast / residual add) kernels of PyTorch.     */
+int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_bc, const float *weight,
+                            const float *bias, float *sum_out, float *y, int B, int C, int HW, int groups,
+                            float eps, int apply_silu, void *stream);
 
 /* Image post-processing of the test drivers (iadb_bn.py:796-816, ddim_diffusers.py:687-688):
  * out_u8[b,h,w,c] = round(clamp(x[b,c,h,w]/2 + 0.5, 0, 1) * 255), NCHW fp32 -> NHWC uint8. */

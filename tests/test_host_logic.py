@@ -200,3 +200,5 @@ def test_streamk_schedule_is_consistent():
                 for sms in (148, 132, 1, 2, 7, 33, 4096):
                     rc = lib.bndm_debug_streamk_check(n_tiles, dense, n_colblk, sms)
                     assert rc == 0, (n_tiles, dense, n_colblk, sms, lib.bndm_last_error())
+                    rc = lib.bndm_debug_streamk_check_sub(n_tiles, dense, n_colblk, sms, 2)    # 64-k pipeline stages
+                    assert rc == 0, (n_tiles, dense, n_colblk, sms, "sub=2", lib.bndm_last_error())

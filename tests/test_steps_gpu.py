@@ -177,3 +177,56 @@ def test_full_size_unet_sampling_graph_equals_eager_short():
     # and the oracle loop with the SAME module on the same device (parity ladder step 3)
     c = osam.sample_iadb_utils(model, x0, 4, "sigmoid", (1000.0, 0.0, 3.0), 6, "gaussianBN", "train")
     np.testing.assert_allclose(a.cpu().numpy(), c.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------ K5: fused GroupNorm (+adds) + SiLU, NHWC
+@pytest.mark.parametrize("B,C,H", [(3, 128, 64), (2, 256, 16), (2, 384, 8), (1, 512, 4), (2, 1024, 2), (2, 768, 8), (5, 128, 32)])
+@pytest.mark.parametrize("mode", ["plain", "add_bc", "res_sum", "nosilu"])
+def test_groupnorm_silu_nhwc_matches_torch(B, C, H, mode):
+    from bndm_b200.fused_unet import groupnorm_silu_nhwc
+    torch.manual_seed(B * 1000 + C + H)
+    x = (torch.randn(B, C, H, H, device=DEV) * 1.7 + 0.6).contiguous(memory_format=torch.channels_last)
+    norm = torch.nn.GroupNorm(32, C, eps=1e-5).to(DEV)
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(C)); norm.bias.copy_(torch.randn(C))
+    add_bc = torch.randn(B, C, device=DEV) if mode == "add_bc" else None
+    res = torch.randn_like(x) if mode == "res_sum" else None
+    out = groupnorm_silu_nhwc(x, norm, add_bc=add_bc, res=res, want_sum=(mode == "res_sum"), silu=(mode != "nosilu"))
+    s = x if res is None else x + res
+    if add_bc is not None:
+        s = s + add_bc[:, :, None, None]
+    with torch.no_grad():
+        want = norm(s)
+        want64 = torch.nn.functional.group_norm(s.double(), 32, norm.weight.double(), norm.bias.double(), 1e-5)
+        if mode != "nosilu":
+            want, want64 = torch.nn.functional.silu(want), torch.nn.functional.silu(want64)
+    if mode == "res_sum":
+        y, ssum = out
+        assert torch.equal(ssum, s)
+    else:
+        y = out
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    err_ours = (y.double() - want64).abs().max().item()
+    err_torch = (want.double() - want64).abs().max().item()
+    assert err_ours <= max(2.0 * err_torch, 5e-6), (err_ours, err_torch)
+    y2 = groupnorm_silu_nhwc(x, norm, add_bc=add_bc, res=res, silu=(mode != "nosilu"))
+    assert torch.equal(y2, y), "fixed-order statistics must be bit-reproducible"
+
+
+def test_fused_unet_matches_plain_unet():
+    from bndm_b200.fused_unet import fuse_unet
+    from bndm_b200.unet import get_model
+    torch.manual_seed(0)
+    model = get_model(3, 6, 64).to(DEV).eval()
+    fused = fuse_unet(model)
+    x = torch.randn(4, 3, 64, 64, device=DEV)
+    t = torch.tensor([0.9, 0.5, 0.25, 0.004], device=DEV)
+    with torch.no_grad():
+        want = model(x, t, return_dict=False)[0]
+        got = fused(x, t, return_dict=False)[0]
+        again = fused(x, t).sample
+    assert got.shape == want.shape and got.is_contiguous()
+    scale = want.abs().max().item()
+    # same cuDNN TF32 convolutions (possibly other algorithms in NHWC) + fp32 round-off of the norms
+    assert (got - want).abs().max().item() < 2e-2 * scale, ((got - want).abs().max().item(), scale)
+    assert torch.equal(got, again)

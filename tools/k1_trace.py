@@ -11,11 +11,13 @@ L = torch.from_numpy(hashed_tril(seed=0)).to(dev)
 h = bb.prepare_L(L, max_columns=192)
 trace = torch.zeros(148 * 24, dtype=torch.int64, device=dev)
 _lib.check(_lib.load().bndm_debug_set_trace(h._h, _lib.ptr(trace)), "trace")
-flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+flush_buf = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device=dev)
+flush_sink = torch.zeros((), dtype=torch.float32, device=dev)
+WRITE_FLUSH = bool(os.environ.get("WRITE_FLUSH"))
 for B in (4, 64):
     x = torch.randn(B, 3, 64, 64, device=dev); g = torch.rand(B, device=dev)
     for it in range(3):
-        flush.zero_()
+        flush_buf.zero_() if WRITE_FLUSH else torch.sum(flush_buf, dim=0, out=flush_sink)
         trace.zero_()
         bb.get_noise_v2(dev, x, h, g, None, "gaussianBN", "train", True, want=("noise",))
         torch.cuda.synchronize()
@@ -30,7 +32,8 @@ for B in (4, 64):
                        ("epilogue done -> exit", 5, 6)):
         d = t[:, b] - t[:, a]
         print(f"   {name:40s} mean {d.mean() / ghz / 1e3:6.2f} us   min {d.min() / ghz / 1e3:6.2f}   max {d.max() / ghz / 1e3:6.2f}")
-    for name, k in (("producer: waiting for a free stage", 20), ("issuer: waiting for operands", 18),
+    for name, k in (("producer: waiting for a free stage", 20), ("issuer: waiting for operands", 18), ("issuer: waiting for a drained TMEM buffer", 19),
+                    ("issuer: operand wait + MMA issue + commit", 21),
                     ("converter: waiting for TMA", 17), ("converter: converting (incl. fence + arrive)", 16)):
         print(f"   {name:44s} mean {t[:, k].mean() / ghz / 1e3:6.2f} us total per CTA")
     if t[:, 13].max() > 0:

@@ -22,12 +22,26 @@ p.add_argument("--res", type=int, default=64)
 p.add_argument("--iters", type=int, default=3)
 p.add_argument("--k2", action="store_true")
 p.add_argument("--no-flush", action="store_true")
+p.add_argument("--flush", choices=["read", "write"], default="read",
+               help="read: a 512 MB reduction leaves L2 full of CLEAN lines (like ncu's cache control); write: a memset leaves it full of DIRTY lines that must be written back while the kernel streams")
 args = p.parse_args()
 
 dev = torch.device("cuda:0")
 L = torch.from_numpy(hashed_tril(seed=0)).to(dev)
 h = bb.prepare_L(L, max_columns=max(args.B) * args.C * (4 if args.res == 128 else 1))
-flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+flush_buf = torch.zeros(128 * 1024 * 1024, dtype=torch.float32, device=dev)
+flush_sink = torch.zeros((), dtype=torch.float32, device=dev)
+
+
+class _Flush:
+    def zero_(self):
+        if args.flush == "write":
+            flush_buf.zero_()
+        else:
+            torch.sum(flush_buf, dim=0, out=flush_sink)
+
+
+flush = _Flush()
 
 
 def timed(fn, n):

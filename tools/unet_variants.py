@@ -41,7 +41,15 @@ ms, y0 = bench(base, x, t)
 print(f"fp32 NCHW (conv TF32, matmul fp32)  graph : {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s")
 ms, _ = bench(base, x, t, graph=False)
 print(f"fp32 NCHW eager                           : {ms:8.3f} ms")
+from bndm_b200.fused_unet import fuse_unet
+fused = fuse_unet(base)
+ms, y = bench(fused, x, t)
+print(f"FUSED channels-last + K5 (graph)          : {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s maxdiff {(y - y0).abs().max().item():.2e}")
+ms, y = bench(fused, x, t, graph=False)
+print(f"FUSED eager                               : {ms:8.3f} ms")
 torch.backends.cudnn.benchmark = True
+ms, y = bench(fused, x, t)
+print(f"FUSED cudnn.benchmark (graph)             : {ms:8.3f} ms  {fl / ms / 1e9:7.1f} TFLOP/s maxdiff {(y - y0).abs().max().item():.2e}")
 ms, y = bench(base, x, t)
 print(f"fp32 NCHW cudnn.benchmark                 : {ms:8.3f} ms  maxdiff {(y - y0).abs().max().item():.2e}")
 m2 = get_model(3, 6, 64).to(dev).eval(); m2.load_state_dict(base.state_dict()); m2 = m2.to(memory_format=torch.channels_last)
