@@ -53,6 +53,9 @@ def parse_args():
     p.add_argument("--nb-steps", type=int, default=250, help="denoising steps per sampling run (configs[1]: 250)")
     p.add_argument("--unet-dtype", choices=["fp32", "bf16"], default="fp32",
                    help="fp32 = the reference's numerics (cuDNN TF32 conv allowed, torch default)")
+    p.add_argument("--unet", choices=["fused", "plain"], default="fused",
+                   help="fused = channels-last evaluation with the K5/K6 kernels (bndm_b200.fused_unet); plain = the "
+                        "stock PyTorch module (NCHW)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the get_noise micro section")
     p.add_argument("--cpu-batch", type=int, default=8)
@@ -188,6 +191,9 @@ def workload_config(args, where):
             "res": RES, "batch_per_gpu": args.batch, "nb_steps": args.nb_steps, "device": where,
             "unet_dtype": ("fp32 weights/activations, cuDNN conv TF32 allowed (torch default, as the reference)"
                            if args.unet_dtype == "fp32" else "bf16 weights/activations"),
+            "unet_eval": ("channels-last, GroupNorm+SiLU(+time-embedding/bias adds) and bias+residual fused in "
+                          "libbndm_b200.so (K5/K6), convolutions = cuDNN" if (args.unet == "fused" and args.unet_dtype == "fp32")
+                          else "stock PyTorch module"),
             "l2": "no explicit flush in the sampling loop: one denoising step streams >1 GB of UNet activations and "
                   "455 MB of weights through the 126 MB L2; the get_noise micro section flushes L2 between iterations"}
 
@@ -232,6 +238,9 @@ def run_ours(args):
     flops_per_image = count_forward_flops(model, RES, RES)
     if args.unet_dtype == "bf16":
         model = model.to(torch.bfloat16)
+    elif args.unet == "fused":
+        from bndm_b200.fused_unet import fuse_unet
+        model = fuse_unet(model)
 
     gamma_T = bb.get_scheduler_gamma(torch.full((B,), float(T)), "sigmoid", GAMMA_PARAMS, T).to(dev)   # == 1
     sampler = bb.IadbSampler(model, (B, CH, RES, RES), T, "sigmoid", GAMMA_PARAMS, OUT_CH, "gaussianBN", device=dev,
@@ -341,9 +350,10 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": white_bytes,
                     "d2h_bytes_per_step": white_bytes, "ms_per_step": ms_e2e / args.steps,
                     "api": "bb.get_noise_v2(...) + bb.sample_iadb(..., use_graph=True); pinned host in/out"},
-            "gpu_launches": args.steps * (3 + T),
-            "gpu_launches_note": "per step: K1a pack + K1b contraction + K1c epilogue + 250 x K2 (UNet kernels are "
-                                 "cuDNN/cuBLAS/ATen, not counted)",
+            "gpu_launches": args.steps * (3 + T * (1 + (getattr(model, "kernels_per_forward", 0) or 0))),
+            "gpu_launches_note": f"per step: K1a pack + K1b contraction + K1c combine + {T} x (K2 + "
+                                 f"{getattr(model, 'kernels_per_forward', 0) or 0} K5/K6 launches inside the UNet forward); "
+                                 "cuDNN/cuBLAS/ATen kernels are not counted",
             "clocks": clock_info, "roofline": roofline, "roofline_step": roofline_step,
             "unet": {"gflop_per_image_forward": flops_per_image / 1e9, "achieved_tflops": unet_tflops,
                      "frac_of_bf16_sustained_peak": unet_tflops / pk["bf16_tflops_sustained"],

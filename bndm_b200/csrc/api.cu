@@ -507,9 +507,18 @@ int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_s
   return rc;
 }
 
-int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_bc, const float *weight, const float *bias,
-                            float *sum_out, float *y, int B, int C, int HW, int groups, float eps, int apply_silu,
-                            void *stream) {
+int bndm_add_bias_nhwc_f32(const float *a, const float *b, const float *bias, float *out, int64_t n, int C, void *stream) {
+  if (!a || !b || !bias || !out || n < 1 || C < 4 || C % 4 != 0 || n % C != 0) { set_error("add_bias: bad argument"); return BNDM_ERR_ARG; }
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(bias) |
+       reinterpret_cast<uintptr_t>(out)) % 16 != 0) { set_error("add_bias: pointers must be 16-byte aligned"); return BNDM_ERR_ARG; }
+  CK(launch_add_bias_nhwc(a, b, bias, out, (size_t)n, C, (cudaStream_t)stream));
+  return BNDM_OK;
+}
+
+int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_bc, int add_bc_stride, const float *weight,
+                            const float *bias, float *sum_out, float *y, int B, int C, int HW, int groups, float eps,
+                            int apply_silu, void *stream) {
+  if (add_bc && (add_bc_stride < C || add_bc_stride % 4 != 0)) { set_error("groupnorm: bad add_bc stride"); return BNDM_ERR_ARG; }
   if (!x || !weight || !bias || !y || B < 1 || C < 1 || HW < 1 || groups < 1) { set_error("groupnorm: bad argument"); return BNDM_ERR_ARG; }
   if (C % groups != 0 || (C / groups) % 4 != 0) {
     set_error("groupnorm: channels per group must be a multiple of 4 (C=%d, groups=%d)", C, groups);
@@ -521,7 +530,7 @@ int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_b
   if (add_bc) al |= reinterpret_cast<uintptr_t>(add_bc);
   if (sum_out) al |= reinterpret_cast<uintptr_t>(sum_out);
   if (al % 16 != 0) { set_error("groupnorm: pointers must be 16-byte aligned"); return BNDM_ERR_ARG; }
-  cudaError_t e = launch_groupnorm_nhwc(x, res, add_bc, weight, bias, sum_out, y, B, C, HW, groups, eps, apply_silu, (cudaStream_t)stream);
+  cudaError_t e = launch_groupnorm_nhwc(x, res, add_bc, add_bc_stride, weight, bias, sum_out, y, B, C, HW, groups, eps, apply_silu, (cudaStream_t)stream);
   if (e == cudaErrorInvalidValue) { set_error("groupnorm: unsupported shape C=%d groups=%d", C, groups); return BNDM_ERR_UNSUPPORTED; }
   CK(e);
   return BNDM_OK;

@@ -15,7 +15,11 @@
 // transposition.  A thread owns one float4 channel quad (always inside one group since
 // channels-per-group is a multiple of 4) and walks the pixels; statistics are per-thread shifted
 // sums merged with Chan's parallel-variance formula in a FIXED order (bit-reproducible).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace bndm {
 
@@ -23,6 +27,7 @@ struct GnArgs {
   const float *x, *res, *add_bc, *weight, *bias;
   float *sum_out, *y;
   int B, C, HW, cpg;       // cpg = channels per group (multiple of 4)
+  int add_stride;          // floats between consecutive samples' rows of add_bc (>= C)
   int cblk;                // channels per CTA (multiple of 32 and of cpg)
   float eps;
   int silu;
@@ -43,7 +48,25 @@ __device__ __forceinline__ Moments merge(const Moments &a, const Moments &b) {
   return r;
 }
 
-__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+// Block-wide merge of per-thread moments into per-group moments, fixed order (binary tree over the
+// nt / q threads that share a channel quad, then the group's quads left to right).
+// s_part: [nt] per-thread moments (clobbered); result for group g in s_out[g], g < n_groups.
+__device__ __forceinline__ void block_group_moments(Moments *s_part, Moments *s_out, int tid, int nt, int q, int qpg, int n_groups) {
+  const int k = tid / q, K = nt / q;
+  for (int stride = 1; stride < K; stride <<= 1) {
+    __syncthreads();
+    if ((k & (2 * stride - 1)) == 0 && k + stride < K) s_part[tid] = merge(s_part[tid], s_part[tid + stride * q]);
+  }
+  __syncthreads();
+  if (tid < n_groups) {
+    Moments acc = s_part[tid * qpg];
+    for (int t = 1; t < qpg; ++t) acc = merge(acc, s_part[tid * qpg + t]);
+    s_out[tid] = acc;
+  }
+}
+
+// SiLU with the SFU exponential and reciprocal: relative error ~1e-6, far below the TF32 convolutions around it
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 constexpr int kGnMaxThreads = 256;
 
@@ -67,7 +90,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_kernel(GnArgs a)
   float4 *s4 = a.sum_out ? reinterpret_cast<float4 *>(a.sum_out + base) : nullptr;
   const int rowq = a.C >> 2;                      // float4 stride between pixels
   float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (a.add_bc) add = __ldg(reinterpret_cast<const float4 *>(a.add_bc + (size_t)b * a.C + c));
+  if (a.add_bc) add = __ldg(reinterpret_cast<const float4 *>(a.add_bc + (size_t)b * a.add_stride + c));
 
   // ---- pass 1: s = x (+ res) (+ add), shifted sums -------------------------------------------
   float shift = 0.f, sum = 0.f, sq = 0.f, cnt = 0.f;
@@ -105,21 +128,11 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_kernel(GnArgs a)
   m.mean = cnt > 0.f ? shift + sum / cnt : 0.f;
   m.m2 = cnt > 0.f ? fmaxf(sq - sum * sum / cnt, 0.f) : 0.f;
   s_part[tid] = m;
-  __syncthreads();
-  // fixed-order merge in two levels: quad column (threads with the same cq), then the group's quads
-  __shared__ Moments s_col[kGnMaxThreads];
-  if (tid < q) {
-    Moments acc = s_part[tid];
-    for (int t = tid + q; t < (int)blockDim.x; t += q) acc = merge(acc, s_part[t]);
-    s_col[tid] = acc;
-  }
-  __syncthreads();
+  __shared__ Moments s_grp[32];
+  block_group_moments(s_part, s_grp, tid, blockDim.x, q, a.cpg >> 2, n_groups);
   if (tid < n_groups) {
-    const int qpg = a.cpg >> 2;                   // quads per group
-    Moments acc = s_col[tid * qpg];
-    for (int t = 1; t < qpg; ++t) acc = merge(acc, s_col[tid * qpg + t]);
-    s_mean[tid] = acc.mean;
-    s_rstd[tid] = rsqrtf(acc.m2 / acc.n + a.eps);
+    s_mean[tid] = s_grp[tid].mean;
+    s_rstd[tid] = rsqrtf(s_grp[tid].m2 / s_grp[tid].n + a.eps);
   }
   __syncthreads();
 
@@ -162,12 +175,138 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_kernel(GnArgs a)
   }
 }
 
+// ---- cluster variant (the fast path) ----------------------------------------------------------
+// A thread-block cluster of P CTAs shares one (sample, channel block): CTA `rank` stages its slab of
+// pixels in SHARED MEMORY with cp.async (every byte of the slab is in flight at once -- the
+// single-CTA kernel above is latency-bound: it keeps ~16 KiB in flight per SM), computes the
+// moments of its slab, the P partial moments are merged in rank order through distributed shared
+// memory, and the slab is normalised straight out of shared memory.  HBM traffic: one read, one
+// write.  Requires res == NULL and sum_out == NULL (the register kernel handles those).
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(GnArgs a, int P, int ppc) {
+  extern __shared__ __align__(16) float4 tile[];   // [pixels of this CTA][q] channel quads
+  __shared__ Moments s_part[kGnMaxThreads];
+  __shared__ Moments s_grp[32];                     // this CTA's moments per group (read by the whole cluster)
+  __shared__ float s_mean[32], s_rstd[32];
+
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  const int c0 = (blockIdx.x / P) * a.cblk;
+  const int q = a.cblk >> 2;
+  const int tid = threadIdx.x, nt = blockDim.x;     // nt is a multiple of q
+  const int px0 = rank * ppc;
+  const int npx = max(0, min(ppc, a.HW - px0));
+  const int n_quads = npx * q;
+  const int rowq = a.C >> 2;
+  const float4 *x4 = reinterpret_cast<const float4 *>(a.x + ((size_t)b * a.HW + px0) * a.C + c0);
+
+  // nt is a multiple of q: thread tid always handles quad cq = tid % q, pixels tid / q + k (nt / q)
+  const int cq = tid % q;
+  const int prow = tid / q, pstep = nt / q;
+  {
+    const float4 *src = x4 + (size_t)prow * rowq + cq;
+    const size_t step = (size_t)pstep * rowq;
+    for (int i = tid; i < n_quads; i += nt, src += step) cp_async16(&tile[i], src);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+
+  const int c = c0 + cq * 4;
+  const int g_local = (cq * 4) / a.cpg;
+  const int n_groups = a.cblk / a.cpg;
+  float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.add_bc) add = __ldg(reinterpret_cast<const float4 *>(a.add_bc + (size_t)b * a.add_stride + c));
+  const float4 w = __ldg(reinterpret_cast<const float4 *>(a.weight + c));
+  const float4 bi = __ldg(reinterpret_cast<const float4 *>(a.bias + c));
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- moments of this CTA's slab (s = x + add is written back so pass 2 reads s) --------------
+  float shift = 0.f, sum = 0.f, sq = 0.f, cnt = 0.f;
+  if (tid < n_quads) shift = tile[tid].x + add.x;
+  for (int i = tid; i < n_quads; i += nt) {
+    float4 s = tile[i];
+    s.x += add.x; s.y += add.y; s.z += add.z; s.w += add.w;
+    if (a.add_bc) tile[i] = s;
+    const float d0 = s.x - shift, d1 = s.y - shift, d2 = s.z - shift, d3 = s.w - shift;
+    sum += (d0 + d1) + (d2 + d3);
+    sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    cnt += 4.f;
+  }
+  Moments m;
+  m.n = cnt;
+  m.mean = cnt > 0.f ? shift + sum / cnt : 0.f;
+  m.m2 = cnt > 0.f ? fmaxf(sq - sum * sum / cnt, 0.f) : 0.f;
+  s_part[tid] = m;
+  block_group_moments(s_part, s_grp, tid, nt, q, a.cpg >> 2, n_groups);
+  cluster.sync();                                   // every CTA's s_grp is complete and visible
+  if (tid < n_groups) {
+    Moments acc = {0.f, 0.f, 0.f};
+    for (int r = 0; r < P; ++r) {                   // rank order: every CTA computes the same bits
+      const Moments *remote = cluster.map_shared_rank(s_grp, r);
+      acc = merge(acc, remote[tid]);
+    }
+    s_mean[tid] = acc.mean;
+    s_rstd[tid] = rsqrtf(acc.m2 / acc.n + a.eps);
+  }
+  cluster.sync();                                   // nobody leaves (or reuses smem) while a peer still reads it
+
+  // ---- normalise + affine + activation out of shared memory -----------------------------------
+  const float mean = s_mean[g_local], rstd = s_rstd[g_local];
+  const float4 sc = make_float4(rstd * w.x, rstd * w.y, rstd * w.z, rstd * w.w);
+  float4 *y4 = reinterpret_cast<float4 *>(a.y + ((size_t)b * a.HW + px0) * a.C + c0) + (size_t)prow * rowq + cq;
+  const size_t ystep = (size_t)pstep * rowq;
+#pragma unroll 4
+  for (int i = tid; i < n_quads; i += nt, y4 += ystep) {
+    const float4 s = tile[i];
+    float4 o;
+    o.x = (s.x - mean) * sc.x + bi.x;
+    o.y = (s.y - mean) * sc.y + bi.y;
+    o.z = (s.z - mean) * sc.z + bi.z;
+    o.w = (s.w - mean) * sc.w + bi.w;
+    if (a.silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+    *y4 = o;
+  }
+}
+
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
-cudaError_t launch_groupnorm_nhwc(const float *x, const float *res, const float *add_bc, const float *weight,
+// K6: out = a + (b + bias[c]) on NHWC activations: the convolution bias and the residual add of
+// a ResnetBlock2D in one pass (PyTorch: a bias-add pass inside conv2, then the add).
+__global__ void __launch_bounds__(256) add_bias_nhwc_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b,
+                                                            const float4 *__restrict__ bias, float4 *__restrict__ out,
+                                                            size_t n4, int cq) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const float4 x = a[i], y = __ldg(b + i), z = __ldg(bias + (i % cq));
+    float4 o;
+    o.x = __fadd_rn(x.x, __fadd_rn(y.x, z.x));
+    o.y = __fadd_rn(x.y, __fadd_rn(y.y, z.y));
+    o.z = __fadd_rn(x.z, __fadd_rn(y.z, z.z));
+    o.w = __fadd_rn(x.w, __fadd_rn(y.w, z.w));
+    out[i] = o;
+  }
+}
+
+cudaError_t launch_add_bias_nhwc(const float *a, const float *b, const float *bias, float *out, size_t n, int C, cudaStream_t s) {
+  const size_t n4 = n / 4;
+  size_t blocks = (n4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  add_bias_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(b),
+                                                        reinterpret_cast<const float4 *>(bias), reinterpret_cast<float4 *>(out), n4,
+                                                        C / 4);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_groupnorm_nhwc(const float *x, const float *res, const float *add_bc, int add_stride, const float *weight,
                                   const float *bias, float *sum_out, float *y, int B, int C, int HW, int groups, float eps,
                                   int silu, cudaStream_t s) {
   GnArgs a;
+  a.add_stride = add_stride;
   a.x = x; a.res = res; a.add_bc = add_bc; a.weight = weight; a.bias = bias; a.sum_out = sum_out; a.y = y;
   a.B = B; a.C = C; a.HW = HW; a.cpg = C / groups; a.eps = eps; a.silu = silu;
   int cblk = a.cpg / gcd_i(a.cpg, 32) * 32;        // lcm(cpg, 32): whole groups and whole 128-byte lines
@@ -176,6 +315,32 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *res, const float 
   const int q = cblk / 4;
   if (q > kGnMaxThreads || cblk / a.cpg > 32) return cudaErrorInvalidValue;
   const int threads = kGnMaxThreads / q * q;
+
+  if (!res && !sum_out) {
+    // cluster path: P CTAs per (sample, channel block), slab of HW / P pixels in shared memory
+    const size_t row_bytes = (size_t)cblk * 4;
+    int P = 1;
+    while (P < 8 && ((size_t)((HW + P - 1) / P) * row_bytes > 64 * 1024)) P *= 2;
+    const int ppc = (HW + P - 1) / P;
+    const size_t smem = (size_t)ppc * row_bytes;
+    if (smem <= 200 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(groupnorm_nhwc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e != cudaSuccess) return e;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)(P * (C / cblk)), (unsigned)B);
+      cfg.blockDim = dim3((unsigned)threads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = (unsigned)P;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      return cudaLaunchKernelEx(&cfg, groupnorm_nhwc_cluster_kernel, a, P, ppc);
+    }
+  }
   dim3 grid(C / cblk, B);
   groupnorm_nhwc_kernel<<<grid, threads, 0, s>>>(a);
   return cudaGetLastError();

@@ -13,7 +13,8 @@ weights into channels-last form) and evaluates the same network with
   * every ``SiLU(GroupNorm(.))`` -- and the ``+ time_emb_proj(temb)`` / conv1-bias adds in front
     of norm2 -- as ONE launch of ``bndm_groupnorm_nhwc_f32`` (csrc/groupnorm.cu),
   * conv1's bias folded into the per-sample time-embedding vector (a (B, C) add instead of a
-    full activation pass).
+    full activation pass), all 30 ``time_emb_proj`` linears evaluated as ONE GEMM per forward,
+  * conv2's bias and the residual add as one pass (``bndm_add_bias_nhwc_f32``).
 Same call conventions as the wrapped model (``model(x, t, return_dict=False)[0]`` /
 ``.sample``); inference only (no autograd through K5).  Results agree with the wrapped module
 to fp32 round-off of the normalisation (the convolutions are the same cuDNN TF32 kernels).
@@ -29,6 +30,9 @@ from . import _lib
 from .unet import UNet2DModel, UNet2DOutput, timestep_embedding
 
 
+LAUNCHES = 0      # launches of libbndm_b200.so kernels issued from this module (host-side count)
+
+
 def groupnorm_silu_nhwc(x, norm, add_bc=None, res=None, want_sum=False, silu=True):
     """y = act(GroupNorm(x (+ res) (+ add_bc[:, :, None, None]))) on a channels-last (B,C,H,W) tensor.
     Returns y, or (y, s) with s = the pre-normalisation sum when ``want_sum``."""
@@ -41,14 +45,33 @@ def groupnorm_silu_nhwc(x, norm, add_bc=None, res=None, want_sum=False, silu=Tru
         raise _lib.BndmError("groupnorm_silu_nhwc: CUDA float32 tensors only (no CPU fallback)")
     y = torch.empty_like(x, memory_format=torch.channels_last)
     s = torch.empty_like(x, memory_format=torch.channels_last) if want_sum else None
+    stride = 0
     if add_bc is not None:
-        add_bc = add_bc.contiguous()
+        if add_bc.dim() != 2 or add_bc.shape != (B, C) or add_bc.stride(1) != 1:      # a column slice is fine
+            add_bc = add_bc.reshape(B, C).contiguous()
+        stride = add_bc.stride(0)
     with torch.cuda.device(x.device):
-        rc = _lib.load().bndm_groupnorm_nhwc_f32(_lib.ptr(x), _lib.ptr(res), _lib.ptr(add_bc), _lib.ptr(norm.weight),
+        rc = _lib.load().bndm_groupnorm_nhwc_f32(_lib.ptr(x), _lib.ptr(res), _lib.ptr(add_bc), stride, _lib.ptr(norm.weight),
                                                  _lib.ptr(norm.bias), _lib.ptr(s), _lib.ptr(y), B, C, H * W, norm.num_groups,
                                                  float(norm.eps), 1 if silu else 0, _lib.current_stream(x.device))
     _lib.check(rc, "bndm_groupnorm_nhwc_f32")
+    global LAUNCHES
+    LAUNCHES += 1
     return (y, s) if want_sum else y
+
+
+def add_bias_residual_nhwc(a, b, bias):
+    """a + (b + bias[:, None, None]) for channels-last (B,C,H,W) tensors: conv bias + residual add in one pass (K6)."""
+    if not (a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous(memory_format=torch.channels_last)):
+        return a + (b + bias[None, :, None, None])
+    out = torch.empty_like(a, memory_format=torch.channels_last)
+    with torch.cuda.device(a.device):
+        rc = _lib.load().bndm_add_bias_nhwc_f32(_lib.ptr(a), _lib.ptr(b), _lib.ptr(bias), _lib.ptr(out), a.numel(), a.shape[1],
+                                                _lib.current_stream(a.device))
+    _lib.check(rc, "bndm_add_bias_nhwc_f32")
+    global LAUNCHES
+    LAUNCHES += 1
+    return out
 
 
 class FusedUNet2D(torch.nn.Module):
@@ -63,18 +86,37 @@ class FusedUNet2D(torch.nn.Module):
         for q in self.m.parameters():
             q.requires_grad_(False)
         self.in_channels, self.out_channels = model.in_channels, model.out_channels
+        # every resnet's time_emb_proj as ONE GEMM per forward: rows of W_all are the concatenated
+        # projection weights; conv1's bias rides along (it is added at the same place, before norm2)
+        blocks = self._resnets()
+        self.temb_w = torch.cat([r.time_emb_proj.weight for r in blocks], 0).contiguous()
+        self.temb_b = torch.cat([r.time_emb_proj.bias + r.conv1.bias for r in blocks], 0).contiguous()
+        self._temb_slices, off = {}, 0
+        for r in blocks:
+            n = r.time_emb_proj.out_features
+            self._temb_slices[id(r)] = (off, off + n)
+            off += n
+
+    def _resnets(self):
+        m = self.m
+        out = []
+        for blk in m.down_blocks:
+            out.extend(blk.resnets)
+        out.extend(m.mid_block.resnets)
+        for blk in m.up_blocks:
+            out.extend(blk.resnets)
+        return out
 
     # -- blocks ---------------------------------------------------------------------------------
-    @staticmethod
-    def _resnet(blk, x, temb_act):
+    def _resnet(self, blk, x, tb_all):
+        lo, hi = self._temb_slices[id(blk)]
         y = groupnorm_silu_nhwc(x, blk.norm1)
-        h = F.conv2d(y, blk.conv1.weight, None, padding=1)
-        tb = F.linear(temb_act, blk.time_emb_proj.weight, blk.time_emb_proj.bias) + blk.conv1.bias    # (B, Cout)
-        y2 = groupnorm_silu_nhwc(h, blk.norm2, add_bc=tb)
-        h2 = blk.conv2(y2)
+        h = F.conv2d(y, blk.conv1.weight, None, padding=1)                 # bias folded into tb_all
+        y2 = groupnorm_silu_nhwc(h, blk.norm2, add_bc=tb_all[:, lo:hi])
+        h2 = F.conv2d(y2, blk.conv2.weight, None, padding=1)               # bias added with the residual (K6)
         if blk.conv_shortcut is not None:
             x = blk.conv_shortcut(x)
-        return x + h2
+        return add_bias_residual_nhwc(x, h2, blk.conv2.bias)
 
     def _down(self, block, h, temb_act):
         skips = []
@@ -97,9 +139,12 @@ class FusedUNet2D(torch.nn.Module):
             h = block.upsamplers[0](h)
         return h
 
+    kernels_per_forward = None      # K5 + K6 launches of one forward (set by the first call)
+
     @torch.no_grad()
     def forward(self, sample, timestep, return_dict=True):
         m = self.m
+        launches_before = LAUNCHES
         t = timestep
         if not torch.is_tensor(t):
             t = torch.tensor([t], dtype=torch.float32 if isinstance(t, float) else torch.int64, device=sample.device)
@@ -108,6 +153,7 @@ class FusedUNet2D(torch.nn.Module):
         t = t * torch.ones(sample.shape[0], dtype=t.dtype, device=t.device)
         emb = timestep_embedding(t, m.time_proj_dim)
         temb_act = F.silu(m.time_embedding(emb))
+        temb_act = torch.addmm(self.temb_b, temb_act, self.temb_w.t())      # (B, sum of Cout): all projections
 
         h = m.conv_in(sample.float().contiguous(memory_format=torch.channels_last))
         skips = [h]
@@ -121,6 +167,8 @@ class FusedUNet2D(torch.nn.Module):
             h = self._up(block, h, skips, temb_act)
         h = m.conv_out(groupnorm_silu_nhwc(h, m.conv_norm_out))
         h = h.contiguous()                                   # NCHW for the step kernels
+        if self.kernels_per_forward is None:
+            self.kernels_per_forward = LAUNCHES - launches_before
         if not return_dict:
             return (h,)
         return UNet2DOutput(sample=h)

@@ -151,12 +151,19 @@ int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_s
  * norm/act sequence of the model built at iadb_bn.py:205-282 and called at :319), one kernel:
  *     s = x (+ res) (+ add_bc[b][c]);  sum_out = s (if non-NULL)
  *     y = act((s - mean_group) * rstd_group * weight[c] + bias[c]),  act = SiLU iff apply_silu
- * x, res, sum_out, y: dev, NHWC [B][HW][C] fp32; add_bc: dev [B][C] or NULL; weight, bias: dev [C].
+ * x, res, sum_out, y: dev, NHWC [B][HW][C] fp32; add_bc: dev, B rows of C floats `add_bc_stride`
+ * floats apart (a column slice of a wider matrix), or NULL; weight, bias: dev [C].
  * groups as torch.nn.GroupNorm (biased variance, eps inside the sqrt); C/groups % 4 == 0.
  * Replaces RowwiseMoments + affine + SiLU (+ broadcast / residual add) kernels of PyTorch.     */
-int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_bc, const float *weight,
-                            const float *bias, float *sum_out, float *y, int B, int C, int HW, int groups,
-                            float eps, int apply_silu, void *stream);
+int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_bc, int add_bc_stride,
+                            const float *weight, const float *bias, float *sum_out, float *y, int B, int C, int HW,
+                            int groups, float eps, int apply_silu, void *stream);
+
+/* K6 -- out = a + (b + bias[c]) on NHWC fp32 activations (n elements, C channels innermost): the
+ * bias of conv2 / conv_shortcut and the residual add of a ResnetBlock2D in one pass, same
+ * association as PyTorch's conv-bias then add.  out may alias a or b.                          */
+int bndm_add_bias_nhwc_f32(const float *a, const float *b, const float *bias, float *out, int64_t n, int C,
+                           void *stream);
 
 /* Image post-processing of the test drivers (iadb_bn.py:796-816, ddim_diffusers.py:687-688):
  * out_u8[b,h,w,c] = round(clamp(x[b,c,h,w]/2 + 0.5, 0, 1) * 255), NCHW fp32 -> NHWC uint8. */

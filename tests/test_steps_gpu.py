@@ -180,7 +180,8 @@ def test_full_size_unet_sampling_graph_equals_eager_short():
 
 
 # ------------------------------------------------------------------ K5: fused GroupNorm (+adds) + SiLU, NHWC
-@pytest.mark.parametrize("B,C,H", [(3, 128, 64), (2, 256, 16), (2, 384, 8), (1, 512, 4), (2, 1024, 2), (2, 768, 8), (5, 128, 32)])
+@pytest.mark.parametrize("B,C,H", [(3, 128, 64), (2, 256, 16), (2, 384, 8), (1, 512, 4), (2, 1024, 2), (2, 768, 8), (5, 128, 32),
+                                   (2, 384, 64), (2, 256, 64), (1, 128, 128)])
 @pytest.mark.parametrize("mode", ["plain", "add_bc", "res_sum", "nosilu"])
 def test_groupnorm_silu_nhwc_matches_torch(B, C, H, mode):
     from bndm_b200.fused_unet import groupnorm_silu_nhwc
@@ -189,7 +190,8 @@ def test_groupnorm_silu_nhwc_matches_torch(B, C, H, mode):
     norm = torch.nn.GroupNorm(32, C, eps=1e-5).to(DEV)
     with torch.no_grad():
         norm.weight.copy_(torch.randn(C)); norm.bias.copy_(torch.randn(C))
-    add_bc = torch.randn(B, C, device=DEV) if mode == "add_bc" else None
+    wide = torch.randn(B, 2 * C + 64, device=DEV)
+    add_bc = wide[:, 32:32 + C] if mode == "add_bc" else None          # a column slice of a wider matrix (row stride != C)
     res = torch.randn_like(x) if mode == "res_sum" else None
     out = groupnorm_silu_nhwc(x, norm, add_bc=add_bc, res=res, want_sum=(mode == "res_sum"), silu=(mode != "nosilu"))
     s = x if res is None else x + res
@@ -211,6 +213,16 @@ def test_groupnorm_silu_nhwc_matches_torch(B, C, H, mode):
     assert err_ours <= max(2.0 * err_torch, 5e-6), (err_ours, err_torch)
     y2 = groupnorm_silu_nhwc(x, norm, add_bc=add_bc, res=res, silu=(mode != "nosilu"))
     assert torch.equal(y2, y), "fixed-order statistics must be bit-reproducible"
+
+
+def test_add_bias_residual_nhwc_is_bit_exact():
+    from bndm_b200.fused_unet import add_bias_residual_nhwc
+    a = torch.randn(3, 128, 16, 16, device=DEV).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(3, 128, 16, 16, device=DEV).contiguous(memory_format=torch.channels_last)
+    bias = torch.randn(128, device=DEV)
+    got = add_bias_residual_nhwc(a, b, bias)
+    assert got.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(got, a + (b + bias[None, :, None, None]))
 
 
 def test_fused_unet_matches_plain_unet():
