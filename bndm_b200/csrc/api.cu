@@ -507,11 +507,15 @@ int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_s
   return rc;
 }
 
-int bndm_add_bias_nhwc_f32(const float *a, const float *b, const float *bias, float *out, int64_t n, int C, void *stream) {
-  if (!a || !b || !bias || !out || n < 1 || C < 4 || C % 4 != 0 || n % C != 0) { set_error("add_bias: bad argument"); return BNDM_ERR_ARG; }
-  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(bias) |
-       reinterpret_cast<uintptr_t>(out)) % 16 != 0) { set_error("add_bias: pointers must be 16-byte aligned"); return BNDM_ERR_ARG; }
-  CK(launch_add_bias_nhwc(a, b, bias, out, (size_t)n, C, (cudaStream_t)stream));
+int bndm_add_bias_nhwc_f32(const float *a, const float *bias_a, const float *b, const float *bias_b, float *out, int64_t n, int C,
+                           void *stream) {
+  if (!a || !b || !bias_b || !out || n < 1 || C < 4 || C % 4 != 0 || n % C != 0) { set_error("add_bias: bad argument"); return BNDM_ERR_ARG; }
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(bias_b) |
+       reinterpret_cast<uintptr_t>(bias_a) | reinterpret_cast<uintptr_t>(out)) % 16 != 0) {
+    set_error("add_bias: pointers must be 16-byte aligned");
+    return BNDM_ERR_ARG;
+  }
+  CK(launch_add_bias_nhwc(a, bias_a, b, bias_b, out, (size_t)n, C, (cudaStream_t)stream));
   return BNDM_OK;
 }
 

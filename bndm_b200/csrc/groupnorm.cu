@@ -275,14 +275,20 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
-// K6: out = a + (b + bias[c]) on NHWC activations: the convolution bias and the residual add of
-// a ResnetBlock2D in one pass (PyTorch: a bias-add pass inside conv2, then the add).
-__global__ void __launch_bounds__(256) add_bias_nhwc_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b,
-                                                            const float4 *__restrict__ bias, float4 *__restrict__ out,
-                                                            size_t n4, int cq) {
+// K6: out = (a [+ bias_a[c]]) + (b + bias_b[c]) on NHWC activations: the biases of conv_shortcut /
+// conv2 and the residual add of a ResnetBlock2D in one pass (PyTorch: a bias-add pass inside each
+// convolution, then the add); same association, so bit-identical to that sequence.
+__global__ void __launch_bounds__(256) add_bias_nhwc_kernel(const float4 *__restrict__ a, const float4 *__restrict__ bias_a,
+                                                            const float4 *__restrict__ b, const float4 *__restrict__ bias_b,
+                                                            float4 *__restrict__ out, size_t n4, int cq) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-    const float4 x = a[i], y = __ldg(b + i), z = __ldg(bias + (i % cq));
+    float4 x = a[i];
+    const float4 y = __ldg(b + i), z = __ldg(bias_b + (i % cq));
+    if (bias_a) {
+      const float4 w = __ldg(bias_a + (i % cq));
+      x.x = __fadd_rn(x.x, w.x); x.y = __fadd_rn(x.y, w.y); x.z = __fadd_rn(x.z, w.z); x.w = __fadd_rn(x.w, w.w);
+    }
     float4 o;
     o.x = __fadd_rn(x.x, __fadd_rn(y.x, z.x));
     o.y = __fadd_rn(x.y, __fadd_rn(y.y, z.y));
@@ -292,13 +298,14 @@ __global__ void __launch_bounds__(256) add_bias_nhwc_kernel(const float4 *__rest
   }
 }
 
-cudaError_t launch_add_bias_nhwc(const float *a, const float *b, const float *bias, float *out, size_t n, int C, cudaStream_t s) {
+cudaError_t launch_add_bias_nhwc(const float *a, const float *bias_a, const float *b, const float *bias_b, float *out, size_t n,
+                                 int C, cudaStream_t s) {
   const size_t n4 = n / 4;
   size_t blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  add_bias_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(b),
-                                                        reinterpret_cast<const float4 *>(bias), reinterpret_cast<float4 *>(out), n4,
-                                                        C / 4);
+  add_bias_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(bias_a),
+                                                        reinterpret_cast<const float4 *>(b), reinterpret_cast<const float4 *>(bias_b),
+                                                        reinterpret_cast<float4 *>(out), n4, C / 4);
   return cudaGetLastError();
 }
 

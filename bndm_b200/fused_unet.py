@@ -60,14 +60,16 @@ def groupnorm_silu_nhwc(x, norm, add_bc=None, res=None, want_sum=False, silu=Tru
     return (y, s) if want_sum else y
 
 
-def add_bias_residual_nhwc(a, b, bias):
-    """a + (b + bias[:, None, None]) for channels-last (B,C,H,W) tensors: conv bias + residual add in one pass (K6)."""
+def add_bias_residual_nhwc(a, b, bias, bias_a=None):
+    """(a [+ bias_a]) + (b + bias) with per-channel biases, channels-last (B,C,H,W) tensors: conv biases +
+    residual add in one pass (K6)."""
     if not (a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous(memory_format=torch.channels_last)):
-        return a + (b + bias[None, :, None, None])
+        a = a.contiguous(memory_format=torch.channels_last)
+        b = b.contiguous(memory_format=torch.channels_last)
     out = torch.empty_like(a, memory_format=torch.channels_last)
     with torch.cuda.device(a.device):
-        rc = _lib.load().bndm_add_bias_nhwc_f32(_lib.ptr(a), _lib.ptr(b), _lib.ptr(bias), _lib.ptr(out), a.numel(), a.shape[1],
-                                                _lib.current_stream(a.device))
+        rc = _lib.load().bndm_add_bias_nhwc_f32(_lib.ptr(a), _lib.ptr(bias_a), _lib.ptr(b), _lib.ptr(bias), _lib.ptr(out), a.numel(),
+                                                a.shape[1], _lib.current_stream(a.device))
     _lib.check(rc, "bndm_add_bias_nhwc_f32")
     global LAUNCHES
     LAUNCHES += 1
@@ -97,6 +99,12 @@ class FusedUNet2D(torch.nn.Module):
             self._temb_slices[id(r)] = (off, off + n)
             off += n
 
+        self._qkv = {}
+        for mod in self.m.modules():
+            if mod.__class__.__name__ == "Attention":
+                self._qkv[id(mod)] = (torch.cat([mod.to_q.weight, mod.to_k.weight, mod.to_v.weight], 0).contiguous(),
+                                      torch.cat([mod.to_q.bias, mod.to_k.bias, mod.to_v.bias], 0).contiguous())
+
     def _resnets(self):
         m = self.m
         out = []
@@ -115,15 +123,32 @@ class FusedUNet2D(torch.nn.Module):
         y2 = groupnorm_silu_nhwc(h, blk.norm2, add_bc=tb_all[:, lo:hi])
         h2 = F.conv2d(y2, blk.conv2.weight, None, padding=1)               # bias added with the residual (K6)
         if blk.conv_shortcut is not None:
-            x = blk.conv_shortcut(x)
+            sc = F.conv2d(x, blk.conv_shortcut.weight, None)              # 1x1; its bias is added in K6 too
+            return add_bias_residual_nhwc(sc, h2, blk.conv2.bias, bias_a=blk.conv_shortcut.bias)
         return add_bias_residual_nhwc(x, h2, blk.conv2.bias)
+
+    def _attention(self, att, x):
+        """diffusers Attention block on a channels-last tensor: K5 without SiLU lands directly in the
+        (B, HW, C) layout the projections want; q/k/v are one GEMM; to_out's bias rides with the residual."""
+        B, C, H, W = x.shape
+        y = groupnorm_silu_nhwc(x, att.group_norm, silu=False)
+        h = y.permute(0, 2, 3, 1).reshape(B, H * W, C)
+        wqkv, bqkv = self._qkv[id(att)]
+        q, k, v = F.linear(h, wqkv, bqkv).split(C, dim=-1)
+
+        def split(t):
+            return t.reshape(B, H * W, att.heads, C // att.heads).transpose(1, 2)
+        o = F.scaled_dot_product_attention(split(q), split(k), split(v))
+        o = F.linear(o.transpose(1, 2).reshape(B, H * W, C), att.to_out[0].weight, None)
+        o = o.reshape(B, H, W, C).permute(0, 3, 1, 2)                      # channels-last view
+        return add_bias_residual_nhwc(x, o, att.to_out[0].bias)
 
     def _down(self, block, h, temb_act):
         skips = []
         for i, resnet in enumerate(block.resnets):
             h = self._resnet(resnet, h, temb_act)
             if block.attentions is not None:
-                h = block.attentions[i](h).contiguous(memory_format=torch.channels_last)
+                h = self._attention(block.attentions[i], h)
             skips.append(h)
         if block.downsamplers is not None:
             h = block.downsamplers[0](h)
@@ -134,7 +159,7 @@ class FusedUNet2D(torch.nn.Module):
         for i, resnet in enumerate(block.resnets):
             h = self._resnet(resnet, torch.cat([h, skips.pop()], dim=1), temb_act)
             if block.attentions is not None:
-                h = block.attentions[i](h).contiguous(memory_format=torch.channels_last)
+                h = self._attention(block.attentions[i], h)
         if block.upsamplers is not None:
             h = block.upsamplers[0](h)
         return h
@@ -161,7 +186,7 @@ class FusedUNet2D(torch.nn.Module):
             h, s = self._down(block, h, temb_act)
             skips.extend(s)
         h = self._resnet(m.mid_block.resnets[0], h, temb_act)
-        h = m.mid_block.attentions[0](h).contiguous(memory_format=torch.channels_last)
+        h = self._attention(m.mid_block.attentions[0], h)
         h = self._resnet(m.mid_block.resnets[1], h, temb_act)
         for block in m.up_blocks:
             h = self._up(block, h, skips, temb_act)

@@ -159,11 +159,12 @@ int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_b
                             const float *weight, const float *bias, float *sum_out, float *y, int B, int C, int HW,
                             int groups, float eps, int apply_silu, void *stream);
 
-/* K6 -- out = a + (b + bias[c]) on NHWC fp32 activations (n elements, C channels innermost): the
- * bias of conv2 / conv_shortcut and the residual add of a ResnetBlock2D in one pass, same
- * association as PyTorch's conv-bias then add.  out may alias a or b.                          */
-int bndm_add_bias_nhwc_f32(const float *a, const float *b, const float *bias, float *out, int64_t n, int C,
-                           void *stream);
+/* K6 -- out = (a [+ bias_a[c]]) + (b + bias_b[c]) on NHWC fp32 activations (n elements, C channels
+ * innermost; bias_a may be NULL): the biases of conv_shortcut / conv2 (or an attention block's
+ * to_out) and the residual add in one pass, same association as PyTorch's conv-bias then add.
+ * out may alias a or b.                                                                        */
+int bndm_add_bias_nhwc_f32(const float *a, const float *bias_a, const float *b, const float *bias_b, float *out,
+                           int64_t n, int C, void *stream);
 
 /* Image post-processing of the test drivers (iadb_bn.py:796-816, ddim_diffusers.py:687-688):
  * out_u8[b,h,w,c] = round(clamp(x[b,c,h,w]/2 + 0.5, 0, 1) * 255), NCHW fp32 -> NHWC uint8. */

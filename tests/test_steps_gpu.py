@@ -223,6 +223,9 @@ def test_add_bias_residual_nhwc_is_bit_exact():
     got = add_bias_residual_nhwc(a, b, bias)
     assert got.is_contiguous(memory_format=torch.channels_last)
     assert torch.equal(got, a + (b + bias[None, :, None, None]))
+    bias_a = torch.randn(128, device=DEV)
+    got = add_bias_residual_nhwc(a, b, bias, bias_a=bias_a)
+    assert torch.equal(got, (a + bias_a[None, :, None, None]) + (b + bias[None, :, None, None]))
 
 
 def test_fused_unet_matches_plain_unet():
