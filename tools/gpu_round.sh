@@ -14,9 +14,9 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3500 --
   python bench.py --steps 1 --warmup 1 --nb-steps 1 --no-cpu-baseline --no-extras > $OUT/ncu_bench.log 2>&1
 python tools/summarize_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1; tail -12 $OUT/launches_summary.txt
 echo "== ncu --set full on our kernels (same command)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|iadb_step_kernel|pack_kernel|combine_kernel' \
-  -c 12 -f -o $OUT/prof_bench python bench.py --steps 1 --warmup 1 --nb-steps 2 --no-cpu-baseline --no-extras > $OUT/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|iadb_step_kernel|pack_kernel|combine_kernel|groupnorm_nhwc|add_bias_nhwc' \
+  -c 24 -f -o $OUT/prof_bench python bench.py --steps 1 --warmup 1 --nb-steps 2 --no-cpu-baseline --no-extras > $OUT/ncu_full.log 2>&1
 echo "== ncu --set full, micro driver (cfg1 B=4 and cfg2 B=64 get_noise, K2 at three shapes)"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|iadb_step_kernel|pack_kernel|combine_kernel' \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gemm_tc_kernel|iadb_step_kernel|pack_kernel|combine_kernel|groupnorm_nhwc|add_bias_nhwc' \
   -c 40 -f -o $OUT/prof_micro env NO_GRAPH_TIMING=1 python tools/k_micro.py --k2 --iters 1 --flush write > $OUT/ncu_micro.log 2>&1
 ls -la $OUT
