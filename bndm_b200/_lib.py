@@ -40,9 +40,10 @@ SIGNATURES = {
     "bndm_debug_set_policy": (C.c_int, [C.c_int, C.c_int]),
     "bndm_debug_streamk_check": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "bndm_debug_streamk_check_sub": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
-    "bndm_groupnorm_nhwc_f32": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-                                          C.c_int, _P]),
-    "bndm_add_bias_nhwc_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
+    "bndm_groupnorm_nhwc_f32": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_float, C.c_int, _P]),
+    "bndm_attention_small_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "bndm_add_bias_nhwc_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
     "bndm_to_uint8_nhwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 

@@ -507,21 +507,37 @@ int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_s
   return rc;
 }
 
-int bndm_add_bias_nhwc_f32(const float *a, const float *bias_a, const float *b, const float *bias_b, float *out, int64_t n, int C,
-                           void *stream) {
-  if (!a || !b || !bias_b || !out || n < 1 || C < 4 || C % 4 != 0 || n % C != 0) { set_error("add_bias: bad argument"); return BNDM_ERR_ARG; }
-  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(bias_b) |
-       reinterpret_cast<uintptr_t>(bias_a) | reinterpret_cast<uintptr_t>(out)) % 16 != 0) {
-    set_error("add_bias: pointers must be 16-byte aligned");
-    return BNDM_ERR_ARG;
+int bndm_attention_small_f32(const float *qkv, float *out, int B, int T, int C, int head_dim, void *stream) {
+  if (!qkv || !out || B < 1 || T < 1 || C < 1) { set_error("attention_small: bad argument"); return BNDM_ERR_ARG; }
+  if ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(out)) % 16 != 0) { set_error("attention_small: misaligned"); return BNDM_ERR_ARG; }
+  cudaError_t e = launch_attention_small(qkv, out, B, T, C, head_dim, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) {
+    set_error("attention_small: head_dim must be 8 and T <= 64 (got head_dim=%d, T=%d)", head_dim, T);
+    return BNDM_ERR_UNSUPPORTED;
   }
-  CK(launch_add_bias_nhwc(a, bias_a, b, bias_b, out, (size_t)n, C, (cudaStream_t)stream));
+  CK(e);
   return BNDM_OK;
 }
 
-int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_bc, int add_bc_stride, const float *weight,
-                            const float *bias, float *sum_out, float *y, int B, int C, int HW, int groups, float eps,
-                            int apply_silu, void *stream) {
+int bndm_add_bias_nhwc_f32(const float *a, const float *a2, const float *bias_a, const float *b, const float *bias_b, float *out,
+                           int64_t n, int C, void *stream) {
+  if (!a || !b || !bias_b || !out || n < 1 || C < 4 || C % 4 != 0 || n % C != 0) { set_error("add_bias: bad argument"); return BNDM_ERR_ARG; }
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(bias_b) |
+       reinterpret_cast<uintptr_t>(bias_a) | reinterpret_cast<uintptr_t>(a2) | reinterpret_cast<uintptr_t>(out)) % 16 != 0) {
+    set_error("add_bias: pointers must be 16-byte aligned");
+    return BNDM_ERR_ARG;
+  }
+  CK(launch_add_bias_nhwc(a, a2, bias_a, b, bias_b, out, (size_t)n, C, (cudaStream_t)stream));
+  return BNDM_OK;
+}
+
+int bndm_groupnorm_nhwc_f32(const float *x, const float *x2, int C1, const float *res, const float *add_bc, int add_bc_stride,
+                            const float *weight, const float *bias, float *sum_out, float *y, int B, int C, int HW, int groups,
+                            float eps, int apply_silu, void *stream) {
+  if (x2 && (C1 < 4 || C1 >= C || C1 % 4 != 0 || reinterpret_cast<uintptr_t>(x2) % 16 != 0)) {
+    set_error("groupnorm: bad second source (C1=%d of C=%d)", C1, C);
+    return BNDM_ERR_ARG;
+  }
   if (add_bc && (add_bc_stride < C || add_bc_stride % 4 != 0)) { set_error("groupnorm: bad add_bc stride"); return BNDM_ERR_ARG; }
   if (!x || !weight || !bias || !y || B < 1 || C < 1 || HW < 1 || groups < 1) { set_error("groupnorm: bad argument"); return BNDM_ERR_ARG; }
   if (C % groups != 0 || (C / groups) % 4 != 0) {
@@ -534,7 +550,7 @@ int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_b
   if (add_bc) al |= reinterpret_cast<uintptr_t>(add_bc);
   if (sum_out) al |= reinterpret_cast<uintptr_t>(sum_out);
   if (al % 16 != 0) { set_error("groupnorm: pointers must be 16-byte aligned"); return BNDM_ERR_ARG; }
-  cudaError_t e = launch_groupnorm_nhwc(x, res, add_bc, add_bc_stride, weight, bias, sum_out, y, B, C, HW, groups, eps, apply_silu, (cudaStream_t)stream);
+  cudaError_t e = launch_groupnorm_nhwc(x, x2, C1, res, add_bc, add_bc_stride, weight, bias, sum_out, y, B, C, HW, groups, eps, apply_silu, (cudaStream_t)stream);
   if (e == cudaErrorInvalidValue) { set_error("groupnorm: unsupported shape C=%d groups=%d", C, groups); return BNDM_ERR_UNSUPPORTED; }
   CK(e);
   return BNDM_OK;

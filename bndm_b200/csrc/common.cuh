@@ -228,9 +228,11 @@ struct DdimArgs {
 };
 
 cudaError_t launch_ddim_step(const DdimArgs &a, cudaStream_t s);
-cudaError_t launch_add_bias_nhwc(const float *a, const float *bias_a, const float *b, const float *bias_b, float *out, size_t n,
-                                 int C, cudaStream_t s);
-cudaError_t launch_groupnorm_nhwc(const float *x, const float *res, const float *add_bc, int add_stride, const float *weight,
+cudaError_t launch_attention_small(const float *qkv, float *out, int B, int T, int C, int head_dim, cudaStream_t s);
+cudaError_t launch_add_bias_nhwc(const float *a, const float *a2, const float *bias_a, const float *b, const float *bias_b,
+                                 float *out, size_t n, int C, cudaStream_t s);
+cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const float *res, const float *add_bc, int add_stride,
+                                  const float *weight,
                                   const float *bias, float *sum_out, float *y, int B, int C, int HW, int groups, float eps,
                                   int silu, cudaStream_t s);
 cudaError_t launch_to_u8(const float *x, uint8_t *out, int B, int C, int HW, cudaStream_t s);

@@ -25,6 +25,8 @@ namespace bndm {
 
 struct GnArgs {
   const float *x, *res, *add_bc, *weight, *bias;
+  const float *x2;         // second source (cluster kernel): channels [C1, C) come from x2 ([B][HW][C - C1]); null = single source
+  int C1;                  // channels held by x (== C when x2 is null)
   float *sum_out, *y;
   int B, C, HW, cpg;       // cpg = channels per group (multiple of 4)
   int add_stride;          // floats between consecutive samples' rows of add_bc (>= C)
@@ -203,14 +205,18 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
   const int npx = max(0, min(ppc, a.HW - px0));
   const int n_quads = npx * q;
   const int rowq = a.C >> 2;
-  const float4 *x4 = reinterpret_cast<const float4 *>(a.x + ((size_t)b * a.HW + px0) * a.C + c0);
 
   // nt is a multiple of q: thread tid always handles quad cq = tid % q, pixels tid / q + k (nt / q)
   const int cq = tid % q;
   const int prow = tid / q, pstep = nt / q;
   {
-    const float4 *src = x4 + (size_t)prow * rowq + cq;
-    const size_t step = (size_t)pstep * rowq;
+    // the quad's channels live in x (row stride C1) or, for a concatenated input, in x2 (row stride C - C1)
+    const int cg0 = c0 + cq * 4;
+    const bool second = a.x2 != nullptr && cg0 >= a.C1;
+    const int srow = second ? a.C - a.C1 : a.C1;
+    const float *sbase = second ? a.x2 + (cg0 - a.C1) : a.x + cg0;
+    const float4 *src = reinterpret_cast<const float4 *>(sbase + ((size_t)b * a.HW + px0 + prow) * srow);
+    const size_t step = (size_t)pstep * (srow >> 2);
     for (int i = tid; i < n_quads; i += nt, src += step) cp_async16(&tile[i], src);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -278,12 +284,17 @@ static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 // K6: out = (a [+ bias_a[c]]) + (b + bias_b[c]) on NHWC activations: the biases of conv_shortcut /
 // conv2 and the residual add of a ResnetBlock2D in one pass (PyTorch: a bias-add pass inside each
 // convolution, then the add); same association, so bit-identical to that sequence.
-__global__ void __launch_bounds__(256) add_bias_nhwc_kernel(const float4 *__restrict__ a, const float4 *__restrict__ bias_a,
-                                                            const float4 *__restrict__ b, const float4 *__restrict__ bias_b,
-                                                            float4 *__restrict__ out, size_t n4, int cq) {
+__global__ void __launch_bounds__(256) add_bias_nhwc_kernel(const float4 *__restrict__ a, const float4 *__restrict__ a2,
+                                                            const float4 *__restrict__ bias_a, const float4 *__restrict__ b,
+                                                            const float4 *__restrict__ bias_b, float4 *__restrict__ out, size_t n4,
+                                                            int cq) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 x = a[i];
+    if (a2) {
+      const float4 u = __ldg(a2 + i);
+      x.x = __fadd_rn(x.x, u.x); x.y = __fadd_rn(x.y, u.y); x.z = __fadd_rn(x.z, u.z); x.w = __fadd_rn(x.w, u.w);
+    }
     const float4 y = __ldg(b + i), z = __ldg(bias_b + (i % cq));
     if (bias_a) {
       const float4 w = __ldg(bias_a + (i % cq));
@@ -298,22 +309,26 @@ __global__ void __launch_bounds__(256) add_bias_nhwc_kernel(const float4 *__rest
   }
 }
 
-cudaError_t launch_add_bias_nhwc(const float *a, const float *bias_a, const float *b, const float *bias_b, float *out, size_t n,
-                                 int C, cudaStream_t s) {
+cudaError_t launch_add_bias_nhwc(const float *a, const float *a2, const float *bias_a, const float *b, const float *bias_b,
+                                 float *out, size_t n, int C, cudaStream_t s) {
   const size_t n4 = n / 4;
   size_t blocks = (n4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  add_bias_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(bias_a),
+  add_bias_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4 *>(a), reinterpret_cast<const float4 *>(a2),
+                                                        reinterpret_cast<const float4 *>(bias_a),
                                                         reinterpret_cast<const float4 *>(b), reinterpret_cast<const float4 *>(bias_b),
                                                         reinterpret_cast<float4 *>(out), n4, C / 4);
   return cudaGetLastError();
 }
 
-cudaError_t launch_groupnorm_nhwc(const float *x, const float *res, const float *add_bc, int add_stride, const float *weight,
-                                  const float *bias, float *sum_out, float *y, int B, int C, int HW, int groups, float eps,
-                                  int silu, cudaStream_t s) {
+cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const float *res, const float *add_bc, int add_stride,
+                                  const float *weight, const float *bias, float *sum_out, float *y, int B, int C, int HW,
+                                  int groups, float eps, int silu, cudaStream_t s) {
   GnArgs a;
   a.add_stride = add_stride;
+  a.x2 = x2;
+  a.C1 = x2 ? C1 : C;
+  if (x2 && (res || sum_out)) return cudaErrorInvalidValue;      // two sources: cluster kernel only
   a.x = x; a.res = res; a.add_bc = add_bc; a.weight = weight; a.bias = bias; a.sum_out = sum_out; a.y = y;
   a.B = B; a.C = C; a.HW = HW; a.cpg = C / groups; a.eps = eps; a.silu = silu;
   int cblk = a.cpg / gcd_i(a.cpg, 32) * 32;        // lcm(cpg, 32): whole groups and whole 128-byte lines
@@ -328,14 +343,25 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *res, const float 
     const size_t row_bytes = (size_t)cblk * 4;
     int P = 1;
     while (P < 8 && ((size_t)((HW + P - 1) / P) * row_bytes > 64 * 1024)) P *= 2;
+    if ((size_t)((HW + P - 1) / P) * row_bytes > 200 * 1024) P = 16;     // 128^2 images: non-portable cluster size
     const int ppc = (HW + P - 1) / P;
     const size_t smem = (size_t)ppc * row_bytes;
     if (smem <= 200 * 1024) {
       cudaError_t e = cudaFuncSetAttribute(groupnorm_nhwc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess && P > 8) e = cudaFuncSetAttribute(groupnorm_nhwc_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       if (e != cudaSuccess) return e;
+      // small slabs: no more thread rows than pixels (shallower merge tree, cheaper CTAs)
+      int rows = kGnMaxThreads / q;
+      if (rows > ppc) rows = ppc;
+      while (rows * q < 32) ++rows;
+      const int nt = rows * q;
+      if (P == 1) {            // a cluster of one: plain launch (this_cluster() degenerates to the CTA)
+        groupnorm_nhwc_cluster_kernel<<<dim3((unsigned)(C / cblk), (unsigned)B), nt, smem, s>>>(a, 1, ppc);
+        return cudaGetLastError();
+      }
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3((unsigned)(P * (C / cblk)), (unsigned)B);
-      cfg.blockDim = dim3((unsigned)threads);
+      cfg.blockDim = dim3((unsigned)nt);
       cfg.dynamicSmemBytes = smem;
       cfg.stream = s;
       cudaLaunchAttribute attr[1];
@@ -348,8 +374,81 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *res, const float 
       return cudaLaunchKernelEx(&cfg, groupnorm_nhwc_cluster_kernel, a, P, ppc);
     }
   }
+  if (x2) return cudaErrorInvalidValue;                           // slab does not fit: caller concatenates first
   dim3 grid(C / cblk, B);
   groupnorm_nhwc_kernel<<<grid, threads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace bndm
+
+// K7: self-attention of the UNet's attention blocks at their tiny sizes (diffusers Attention with
+// attention_head_dim = 8 at 4x4 / 2x2 resolution: T = 16 or 4 tokens, C / 8 heads; iadb_bn.py:216,222).
+// qkv: [B][T][3C] (q | k | v along the last axis, head h = channels 8h .. 8h+7), out: [B][T][C].
+// One thread per (sample, head, query token): scores against the T keys in registers, softmax,
+// weighted sum of the values.  PyTorch dispatches these shapes to a generic flash-attention kernel
+// that takes ~80 us per call at B=64; this is a few microseconds of L2-resident traffic.
+namespace bndm {
+
+constexpr int kAttnMaxT = 64;
+
+template <int D>
+__global__ void __launch_bounds__(256) attention_small_kernel(const float *__restrict__ qkv, float *__restrict__ out, int B, int T,
+                                                              int C, float scale) {
+  const int heads = C / D;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // ((b * T + t) * heads + h)
+  if (idx >= (int64_t)B * T * heads) return;
+  const int h = (int)(idx % heads);
+  const int64_t bt = idx / heads;
+  const int b = (int)(bt / T);
+  const float *q = qkv + bt * 3 * C + h * D;
+  const float *kbase = qkv + (int64_t)b * T * 3 * C + C + h * D;
+  float qv[D];
+#pragma unroll
+  for (int d = 0; d < D; d += 4) {
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(q + d));
+    qv[d] = v.x; qv[d + 1] = v.y; qv[d + 2] = v.z; qv[d + 3] = v.w;
+  }
+  float s[kAttnMaxT];
+  float m = -INFINITY;
+  for (int j = 0; j < T; ++j) {
+    const float *k = kbase + (int64_t)j * 3 * C;
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; d += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4 *>(k + d));
+      acc += qv[d] * v.x + qv[d + 1] * v.y + qv[d + 2] * v.z + qv[d + 3] * v.w;
+    }
+    s[j] = acc * scale;
+    m = fmaxf(m, s[j]);
+  }
+  float denom = 0.f;
+  for (int j = 0; j < T; ++j) {
+    s[j] = expf(s[j] - m);
+    denom += s[j];
+  }
+  const float inv = 1.0f / denom;
+  float o[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) o[d] = 0.f;
+  for (int j = 0; j < T; ++j) {
+    const float *v = kbase + C + (int64_t)j * 3 * C;
+    const float p = s[j] * inv;
+#pragma unroll
+    for (int d = 0; d < D; d += 4) {
+      const float4 w = __ldg(reinterpret_cast<const float4 *>(v + d));
+      o[d] += p * w.x; o[d + 1] += p * w.y; o[d + 2] += p * w.z; o[d + 3] += p * w.w;
+    }
+  }
+  float *dst = out + bt * C + h * D;
+#pragma unroll
+  for (int d = 0; d < D; d += 4) *reinterpret_cast<float4 *>(dst + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
+}
+
+cudaError_t launch_attention_small(const float *qkv, float *out, int B, int T, int C, int head_dim, cudaStream_t s) {
+  if (head_dim != 8 || T > kAttnMaxT || C % head_dim != 0) return cudaErrorInvalidValue;
+  const int64_t n = (int64_t)B * T * (C / head_dim);
+  attention_small_kernel<8><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(qkv, out, B, T, C, 1.0f / sqrtf((float)head_dim));
   return cudaGetLastError();
 }
 

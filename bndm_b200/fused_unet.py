@@ -33,44 +33,66 @@ from .unet import UNet2DModel, UNet2DOutput, timestep_embedding
 LAUNCHES = 0      # launches of libbndm_b200.so kernels issued from this module (host-side count)
 
 
-def groupnorm_silu_nhwc(x, norm, add_bc=None, res=None, want_sum=False, silu=True):
+def groupnorm_silu_nhwc(x, norm, add_bc=None, res=None, want_sum=False, silu=True, x2=None):
     """y = act(GroupNorm(x (+ res) (+ add_bc[:, :, None, None]))) on a channels-last (B,C,H,W) tensor.
-    Returns y, or (y, s) with s = the pre-normalisation sum when ``want_sum``."""
-    B, C, H, W = x.shape
+    Returns y, or (y, s) with s = the pre-normalisation sum when ``want_sum``.
+    ``x2``: the input is ``torch.cat((x, x2), 1)`` -- read from the two tensors, never materialised."""
+    B, C1, H, W = x.shape
+    C = C1 + (x2.shape[1] if x2 is not None else 0)
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
+    if x2 is not None and not x2.is_contiguous(memory_format=torch.channels_last):
+        x2 = x2.contiguous(memory_format=torch.channels_last)
     if res is not None and not res.is_contiguous(memory_format=torch.channels_last):
         res = res.contiguous(memory_format=torch.channels_last)
     if x.dtype != torch.float32 or not x.is_cuda:
         raise _lib.BndmError("groupnorm_silu_nhwc: CUDA float32 tensors only (no CPU fallback)")
-    y = torch.empty_like(x, memory_format=torch.channels_last)
-    s = torch.empty_like(x, memory_format=torch.channels_last) if want_sum else None
+    y = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    s = torch.empty_like(y) if want_sum else None
     stride = 0
     if add_bc is not None:
         if add_bc.dim() != 2 or add_bc.shape != (B, C) or add_bc.stride(1) != 1:      # a column slice is fine
             add_bc = add_bc.reshape(B, C).contiguous()
         stride = add_bc.stride(0)
     with torch.cuda.device(x.device):
-        rc = _lib.load().bndm_groupnorm_nhwc_f32(_lib.ptr(x), _lib.ptr(res), _lib.ptr(add_bc), stride, _lib.ptr(norm.weight),
+        rc = _lib.load().bndm_groupnorm_nhwc_f32(_lib.ptr(x), _lib.ptr(x2), C1, _lib.ptr(res), _lib.ptr(add_bc), stride,
+                                                 _lib.ptr(norm.weight),
                                                  _lib.ptr(norm.bias), _lib.ptr(s), _lib.ptr(y), B, C, H * W, norm.num_groups,
                                                  float(norm.eps), 1 if silu else 0, _lib.current_stream(x.device))
+    if rc == _lib.ERR_UNSUPPORTED and x2 is not None:          # slab too large for the two-source kernel
+        return groupnorm_silu_nhwc(torch.cat([x, x2], 1), norm, add_bc, res, want_sum, silu)
     _lib.check(rc, "bndm_groupnorm_nhwc_f32")
     global LAUNCHES
     LAUNCHES += 1
     return (y, s) if want_sum else y
 
 
-def add_bias_residual_nhwc(a, b, bias, bias_a=None):
-    """(a [+ bias_a]) + (b + bias) with per-channel biases, channels-last (B,C,H,W) tensors: conv biases +
-    residual add in one pass (K6)."""
+def add_bias_residual_nhwc(a, b, bias, bias_a=None, a2=None):
+    """((a [+ a2]) [+ bias_a]) + (b + bias) with per-channel biases, channels-last (B,C,H,W) tensors: conv
+    biases + residual add in one pass (K6)."""
+    if a2 is not None and not a2.is_contiguous(memory_format=torch.channels_last):
+        a2 = a2.contiguous(memory_format=torch.channels_last)
     if not (a.is_contiguous(memory_format=torch.channels_last) and b.is_contiguous(memory_format=torch.channels_last)):
         a = a.contiguous(memory_format=torch.channels_last)
         b = b.contiguous(memory_format=torch.channels_last)
     out = torch.empty_like(a, memory_format=torch.channels_last)
     with torch.cuda.device(a.device):
-        rc = _lib.load().bndm_add_bias_nhwc_f32(_lib.ptr(a), _lib.ptr(bias_a), _lib.ptr(b), _lib.ptr(bias), _lib.ptr(out), a.numel(),
-                                                a.shape[1], _lib.current_stream(a.device))
+        rc = _lib.load().bndm_add_bias_nhwc_f32(_lib.ptr(a), _lib.ptr(a2), _lib.ptr(bias_a), _lib.ptr(b), _lib.ptr(bias),
+                                                _lib.ptr(out), a.numel(), a.shape[1], _lib.current_stream(a.device))
     _lib.check(rc, "bndm_add_bias_nhwc_f32")
+    global LAUNCHES
+    LAUNCHES += 1
+    return out
+
+
+def attention_small(qkv, C, head_dim=8):
+    """softmax(q k^T / sqrt(d)) v for (B, T, 3C) packed projections with tiny T (K7)."""
+    B, T, _ = qkv.shape
+    qkv = qkv.contiguous()
+    out = torch.empty(B, T, C, dtype=torch.float32, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        rc = _lib.load().bndm_attention_small_f32(_lib.ptr(qkv), _lib.ptr(out), B, T, C, head_dim, _lib.current_stream(qkv.device))
+    _lib.check(rc, "bndm_attention_small_f32")
     global LAUNCHES
     LAUNCHES += 1
     return out
@@ -99,6 +121,7 @@ class FusedUNet2D(torch.nn.Module):
             self._temb_slices[id(r)] = (off, off + n)
             off += n
 
+        self._sc_w = {}
         self._qkv = {}
         for mod in self.m.modules():
             if mod.__class__.__name__ == "Attention":
@@ -116,16 +139,30 @@ class FusedUNet2D(torch.nn.Module):
         return out
 
     # -- blocks ---------------------------------------------------------------------------------
-    def _resnet(self, blk, x, tb_all):
+    def _resnet(self, blk, x, tb_all, x2=None):
+        """x2: the block's input is cat((x, x2), 1) (up blocks) -- never materialised: norm1 reads both
+        tensors and the 1x1 conv_shortcut is applied to the two halves separately."""
         lo, hi = self._temb_slices[id(blk)]
-        y = groupnorm_silu_nhwc(x, blk.norm1)
+        y = groupnorm_silu_nhwc(x, blk.norm1, x2=x2)
         h = F.conv2d(y, blk.conv1.weight, None, padding=1)                 # bias folded into tb_all
         y2 = groupnorm_silu_nhwc(h, blk.norm2, add_bc=tb_all[:, lo:hi])
         h2 = F.conv2d(y2, blk.conv2.weight, None, padding=1)               # bias added with the residual (K6)
+        if x2 is not None:
+            w1, w2 = self._sc_split(blk, x.shape[1])
+            sc, sc2 = F.conv2d(x, w1, None), F.conv2d(x2, w2, None)
+            return add_bias_residual_nhwc(sc, h2, blk.conv2.bias, bias_a=blk.conv_shortcut.bias, a2=sc2)
         if blk.conv_shortcut is not None:
             sc = F.conv2d(x, blk.conv_shortcut.weight, None)              # 1x1; its bias is added in K6 too
             return add_bias_residual_nhwc(sc, h2, blk.conv2.bias, bias_a=blk.conv_shortcut.bias)
         return add_bias_residual_nhwc(x, h2, blk.conv2.bias)
+
+    def _sc_split(self, blk, c1):
+        key = (id(blk), c1)
+        if key not in self._sc_w:
+            w = blk.conv_shortcut.weight
+            self._sc_w[key] = (w[:, :c1].contiguous(memory_format=torch.channels_last),
+                               w[:, c1:].contiguous(memory_format=torch.channels_last))
+        return self._sc_w[key]
 
     def _attention(self, att, x):
         """diffusers Attention block on a channels-last tensor: K5 without SiLU lands directly in the
@@ -134,12 +171,16 @@ class FusedUNet2D(torch.nn.Module):
         y = groupnorm_silu_nhwc(x, att.group_norm, silu=False)
         h = y.permute(0, 2, 3, 1).reshape(B, H * W, C)
         wqkv, bqkv = self._qkv[id(att)]
-        q, k, v = F.linear(h, wqkv, bqkv).split(C, dim=-1)
+        qkv = F.linear(h, wqkv, bqkv)                                       # (B, HW, 3C)
+        if C // att.heads == 8 and H * W <= 64:
+            o = attention_small(qkv, C)                                     # K7
+        else:
+            q, k, v = qkv.split(C, dim=-1)
 
-        def split(t):
-            return t.reshape(B, H * W, att.heads, C // att.heads).transpose(1, 2)
-        o = F.scaled_dot_product_attention(split(q), split(k), split(v))
-        o = F.linear(o.transpose(1, 2).reshape(B, H * W, C), att.to_out[0].weight, None)
+            def split(t):
+                return t.reshape(B, H * W, att.heads, C // att.heads).transpose(1, 2)
+            o = F.scaled_dot_product_attention(split(q), split(k), split(v)).transpose(1, 2).reshape(B, H * W, C)
+        o = F.linear(o, att.to_out[0].weight, None)
         o = o.reshape(B, H, W, C).permute(0, 3, 1, 2)                      # channels-last view
         return add_bias_residual_nhwc(x, o, att.to_out[0].bias)
 
@@ -157,7 +198,7 @@ class FusedUNet2D(torch.nn.Module):
 
     def _up(self, block, h, skips, temb_act):
         for i, resnet in enumerate(block.resnets):
-            h = self._resnet(resnet, torch.cat([h, skips.pop()], dim=1), temb_act)
+            h = self._resnet(resnet, h, temb_act, x2=skips.pop())
             if block.attentions is not None:
                 h = self._attention(block.attentions[i], h)
         if block.upsamplers is not None:

@@ -150,21 +150,29 @@ int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_s
 /* K5 -- the UNet's normalisation glue on channels-last activations (diffusers ResnetBlock2D
  * norm/act sequence of the model built at iadb_bn.py:205-282 and called at :319), one kernel:
  *     s = x (+ res) (+ add_bc[b][c]);  sum_out = s (if non-NULL)
+ *     (x2 != NULL: the input is the channel concatenation [x | x2] -- x holds channels [0, C1) as
+ *      [B][HW][C1], x2 the rest as [B][HW][C - C1] -- i.e. torch.cat((x, x2), 1) without the copy;
+ *      res and sum_out must then be NULL)
  *     y = act((s - mean_group) * rstd_group * weight[c] + bias[c]),  act = SiLU iff apply_silu
  * x, res, sum_out, y: dev, NHWC [B][HW][C] fp32; add_bc: dev, B rows of C floats `add_bc_stride`
  * floats apart (a column slice of a wider matrix), or NULL; weight, bias: dev [C].
  * groups as torch.nn.GroupNorm (biased variance, eps inside the sqrt); C/groups % 4 == 0.
  * Replaces RowwiseMoments + affine + SiLU (+ broadcast / residual add) kernels of PyTorch.     */
-int bndm_groupnorm_nhwc_f32(const float *x, const float *res, const float *add_bc, int add_bc_stride,
-                            const float *weight, const float *bias, float *sum_out, float *y, int B, int C, int HW,
-                            int groups, float eps, int apply_silu, void *stream);
+int bndm_groupnorm_nhwc_f32(const float *x, const float *x2, int C1, const float *res, const float *add_bc,
+                            int add_bc_stride, const float *weight, const float *bias, float *sum_out, float *y, int B,
+                            int C, int HW, int groups, float eps, int apply_silu, void *stream);
 
-/* K6 -- out = (a [+ bias_a[c]]) + (b + bias_b[c]) on NHWC fp32 activations (n elements, C channels
- * innermost; bias_a may be NULL): the biases of conv_shortcut / conv2 (or an attention block's
+/* K7 -- softmax(q k^T / sqrt(head_dim)) v for the UNet's attention blocks at their tiny sizes (4x4 / 2x2
+ * resolution, head_dim 8): qkv dev [B][T][3C] (q | k | v on the last axis, head h = channels 8h..8h+7),
+ * out dev [B][T][C].  head_dim must be 8, T <= 64.  Replaces F.scaled_dot_product_attention there. */
+int bndm_attention_small_f32(const float *qkv, float *out, int B, int T, int C, int head_dim, void *stream);
+
+/* K6 -- out = ((a [+ a2]) [+ bias_a[c]]) + (b + bias_b[c]) on NHWC fp32 activations (n elements, C
+ * channels innermost; a2 and bias_a may be NULL): the biases of conv_shortcut / conv2 (or an attention block's
  * to_out) and the residual add in one pass, same association as PyTorch's conv-bias then add.
  * out may alias a or b.                                                                        */
-int bndm_add_bias_nhwc_f32(const float *a, const float *bias_a, const float *b, const float *bias_b, float *out,
-                           int64_t n, int C, void *stream);
+int bndm_add_bias_nhwc_f32(const float *a, const float *a2, const float *bias_a, const float *b, const float *bias_b,
+                           float *out, int64_t n, int C, void *stream);
 
 /* Image post-processing of the test drivers (iadb_bn.py:796-816, ddim_diffusers.py:687-688):
  * out_u8[b,h,w,c] = round(clamp(x[b,c,h,w]/2 + 0.5, 0, 1) * 255), NCHW fp32 -> NHWC uint8. */

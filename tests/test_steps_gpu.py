@@ -215,6 +215,20 @@ def test_groupnorm_silu_nhwc_matches_torch(B, C, H, mode):
     assert torch.equal(y2, y), "fixed-order statistics must be bit-reproducible"
 
 
+@pytest.mark.parametrize("B,C1,C2,H", [(2, 128, 128, 64), (2, 256, 128, 32), (3, 512, 512, 4), (2, 512, 256, 8), (2, 128, 128, 16)])
+def test_groupnorm_two_sources_equals_cat(B, C1, C2, H):
+    from bndm_b200.fused_unet import groupnorm_silu_nhwc
+    a = torch.randn(B, C1, H, H, device=DEV).contiguous(memory_format=torch.channels_last)
+    b = (torch.randn(B, C2, H, H, device=DEV) * 2 - 0.3).contiguous(memory_format=torch.channels_last)
+    norm = torch.nn.GroupNorm(32, C1 + C2).to(DEV)
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(C1 + C2)); norm.bias.copy_(torch.randn(C1 + C2))
+    tb = torch.randn(B, C1 + C2, device=DEV)
+    got = groupnorm_silu_nhwc(a, norm, add_bc=tb, x2=b)
+    want = groupnorm_silu_nhwc(torch.cat([a, b], 1), norm, add_bc=tb)
+    assert torch.equal(got, want)
+
+
 def test_add_bias_residual_nhwc_is_bit_exact():
     from bndm_b200.fused_unet import add_bias_residual_nhwc
     a = torch.randn(3, 128, 16, 16, device=DEV).contiguous(memory_format=torch.channels_last)
@@ -226,6 +240,19 @@ def test_add_bias_residual_nhwc_is_bit_exact():
     bias_a = torch.randn(128, device=DEV)
     got = add_bias_residual_nhwc(a, b, bias, bias_a=bias_a)
     assert torch.equal(got, (a + bias_a[None, :, None, None]) + (b + bias[None, :, None, None]))
+    a2 = torch.randn_like(a)
+    got = add_bias_residual_nhwc(a, b, bias, bias_a=bias_a, a2=a2)
+    assert torch.equal(got, ((a + a2) + bias_a[None, :, None, None]) + (b + bias[None, :, None, None]))
+
+
+@pytest.mark.parametrize("B,T,C", [(3, 16, 512), (2, 4, 512), (5, 64, 64), (1, 1, 8)])
+def test_attention_small_matches_sdpa(B, T, C):
+    from bndm_b200.fused_unet import attention_small
+    qkv = torch.randn(B, T, 3 * C, device=DEV)
+    got = attention_small(qkv, C)
+    q, k, v = (t.reshape(B, T, C // 8, 8).transpose(1, 2) for t in qkv.split(C, dim=-1))
+    want = torch.nn.functional.scaled_dot_product_attention(q.double(), k.double(), v.double()).transpose(1, 2).reshape(B, T, C)
+    np.testing.assert_allclose(got.cpu().numpy(), want.float().cpu().numpy(), rtol=1e-5, atol=2e-6)
 
 
 def test_fused_unet_matches_plain_unet():
@@ -245,3 +272,18 @@ def test_fused_unet_matches_plain_unet():
     # same cuDNN TF32 convolutions (possibly other algorithms in NHWC) + fp32 round-off of the norms
     assert (got - want).abs().max().item() < 2e-2 * scale, ((got - want).abs().max().item(), scale)
     assert torch.equal(got, again)
+
+
+def test_sample_iadb_with_fused_unet_in_a_cuda_graph():
+    """K5/K6/K7 are stream-ordered and allocation-free: the [fused UNet -> K2] step captures into one
+    CUDA graph and replays bit-identically to the eager loop with the same module."""
+    from bndm_b200.fused_unet import fuse_unet
+    from bndm_b200.unet import get_latent_model
+    torch.manual_seed(0)
+    model = fuse_unet(get_latent_model(256, 8).to(DEV).eval())
+    z = torch.randn(2, 4, 32, 32, device=DEV)
+    eager = bb.sample_latent_iadb(model, z, 5, "gaussianBN", 8, use_graph=False)
+    graphed = bb.sample_latent_iadb(model, z, 5, "gaussianBN", 8, use_graph=True)
+    assert torch.equal(eager, graphed)
+    ref = osam.latent_loop(model, z, 5, "gaussianBN", 8)          # the oracle's loop around the same module
+    np.testing.assert_allclose(graphed.cpu().numpy(), ref.cpu().numpy(), rtol=RTOL, atol=ATOL)

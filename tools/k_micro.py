@@ -96,7 +96,7 @@ for B in args.B:
     for want in (("noise",), ("noise", "bn", "wn")):
         ts = timed(lambda: bb.get_noise_v2(dev, x, h, g, None, "gaussianBN", "train", True, want=want), args.iters + 2)
         print(f"get_noise B={B} C={args.C} res={args.res} outputs={len(want)}: us per call = "
-              f"{[round(t, 1) for t in ts]} median {statistics.median(ts[2:]):.1f}", flush=True)
+              f"{[round(t, 1) for t in ts]} median {statistics.median(ts[2:] or ts):.1f}", flush=True)
 
 if args.k2:
     for B, C, Cd, HW in [(64, 3, 6, 4096), (32, 3, 6, 16384), (16, 4, 8, 4096)]:
@@ -106,7 +106,7 @@ if args.k2:
         d = torch.randn(B, Cd, int(HW ** 0.5), int(HW ** 0.5), device=dev)
         ts = timed(lambda: st.step_(x, d), 6)
         nbytes = 4 * B * HW * (2 * C + Cd)
-        med = statistics.median(ts[2:])
+        med = statistics.median(ts[2:] or ts)
         print(f"K2 B={B} C={C} Cd={Cd} HW={HW}: us = {[round(t, 1) for t in ts]} median {med:.1f} "
               f"({nbytes / med / 1e3:.0f} GB/s with event overhead)", flush=True)
 
