@@ -12,7 +12,8 @@ value    whole-job images/sec, white field already resident in HBM when the cloc
 e2e      same metric through the public API (bb.get_noise_v2 + bb.sample_iadb) with HOST
          buffers: pinned host white field -> device, result images -> pinned host, every step.
 roofline the L.z contraction kernel (K1b) timed live with CUDA events on its launch stream
-         inside the timed region; `roofline_step` the same for the IADB update kernel (K2).
+         inside the timed region; `roofline_step` the same for the IADB update kernel (K2);
+         `roofline_glue` the UNet's fused GroupNorm kernel (K5), timed on one eager forward.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo's CUDA path
     python bench.py --impl reference [...]                              # reference CPU path (oracle port)
@@ -309,6 +310,39 @@ def run_ours(args):
     ms_res = float(ms_res.item())
     clock_info = clocks.stop()
 
+    # ---- K5 / K6 / K7 (the UNet's glue kernels, the largest share of device time among the kernels
+    # of libbndm_b200.so): inside the timed steps they run from a CUDA graph, so they are timed live
+    # right after, on the same model / batch / stream: one eager forward with every launch
+    # bracketed by CUDA events
+    roofline_glue = None
+    if args.unet == "fused" and args.unet_dtype == "fp32":
+        from bndm_b200 import fused_unet as fu
+        t_probe = torch.full((B,), 0.5, device=dev)
+        with torch.no_grad():
+            model(whites_dev[0], t_probe, return_dict=False)
+            torch.cuda.synchronize(dev)
+            fu.TIMING = []
+            model(whites_dev[0], t_probe, return_dict=False)
+            torch.cuda.synchronize(dev)
+        recs, fu.TIMING = fu.TIMING, None
+        by = {}
+        for name, nbytes, e0, e1 in recs:
+            d = by.setdefault(name, [0, 0.0, 0, 0.0, 0])
+            ms = e0.elapsed_time(e1)
+            d[0] += nbytes; d[1] += ms; d[2] += 1
+            if nbytes >= 64 * 1024 * 1024:                      # the launches that are not latency-bound
+                d[3] += ms; d[4] += nbytes
+        k5 = by.get("K5", [0, 1e-9, 0, 0.0, 0])
+        roofline_glue = {"kernel": "groupnorm_nhwc_cluster_kernel (K5: fused GroupNorm + SiLU + adds, NHWC)", "bound": "hbm",
+                         "achieved": k5[0] / (k5[1] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": k5[0] / (k5[1] * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                         "bytes_per_forward": k5[0], "ms_per_forward": k5[1], "launches_timed": k5[2],
+                         "achieved_large_launches": (k5[4] / (k5[3] * 1e-3) / 1e9) if k5[3] > 0 else None,
+                         "note": "all K5 launches of one eager forward (B=64), algorithmic bytes = read x once + write y "
+                                 "once; each launch carries ~3 us of event overhead; 'large' = launches moving >= 64 MiB",
+                         "others": {k: {"launches": v[2], "ms_per_forward": v[1], "gbs": v[0] / (v[1] * 1e-3) / 1e9}
+                                    for k, v in by.items() if k != "K5"}}
+
     # ---- end to end through the public API with host buffers
     ms_e2e = timed(step_e2e)
 
@@ -354,7 +388,7 @@ def run_ours(args):
             "gpu_launches_note": f"per step: K1a pack + K1b contraction + K1c combine + {T} x (K2 + "
                                  f"{getattr(model, 'kernels_per_forward', 0) or 0} K5/K6 launches inside the UNet forward); "
                                  "cuDNN/cuBLAS/ATen kernels are not counted",
-            "clocks": clock_info, "roofline": roofline, "roofline_step": roofline_step,
+            "clocks": clock_info, "roofline": roofline, "roofline_step": roofline_step, "roofline_glue": roofline_glue,
             "unet": {"gflop_per_image_forward": flops_per_image / 1e9, "achieved_tflops": unet_tflops,
                      "frac_of_bf16_sustained_peak": unet_tflops / pk["bf16_tflops_sustained"],
                      "images_per_s_ceiling_at_bf16_sustained_peak":

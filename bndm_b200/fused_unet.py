@@ -31,6 +31,19 @@ from .unet import UNet2DModel, UNet2DOutput, timestep_embedding
 
 
 LAUNCHES = 0      # launches of libbndm_b200.so kernels issued from this module (host-side count)
+TIMING = None     # when a list: every K5 / K6 / K7 launch is bracketed by CUDA events on its stream and
+                  # (name, algorithmic bytes, start event, end event) is appended (bench.py's live roofline)
+
+
+def _timed_launch(name, nbytes, device, launch):
+    if TIMING is None:
+        return launch()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(torch.cuda.current_stream(device))
+    rc = launch()
+    e1.record(torch.cuda.current_stream(device))
+    TIMING.append((name, nbytes, e0, e1))
+    return rc
 
 
 def groupnorm_silu_nhwc(x, norm, add_bc=None, res=None, want_sum=False, silu=True, x2=None):
@@ -55,10 +68,10 @@ def groupnorm_silu_nhwc(x, norm, add_bc=None, res=None, want_sum=False, silu=Tru
             add_bc = add_bc.reshape(B, C).contiguous()
         stride = add_bc.stride(0)
     with torch.cuda.device(x.device):
-        rc = _lib.load().bndm_groupnorm_nhwc_f32(_lib.ptr(x), _lib.ptr(x2), C1, _lib.ptr(res), _lib.ptr(add_bc), stride,
-                                                 _lib.ptr(norm.weight),
-                                                 _lib.ptr(norm.bias), _lib.ptr(s), _lib.ptr(y), B, C, H * W, norm.num_groups,
-                                                 float(norm.eps), 1 if silu else 0, _lib.current_stream(x.device))
+        rc = _timed_launch("K5", 8 * y.numel(), x.device, lambda: _lib.load().bndm_groupnorm_nhwc_f32(
+            _lib.ptr(x), _lib.ptr(x2), C1, _lib.ptr(res), _lib.ptr(add_bc), stride, _lib.ptr(norm.weight), _lib.ptr(norm.bias),
+            _lib.ptr(s), _lib.ptr(y), B, C, H * W, norm.num_groups, float(norm.eps), 1 if silu else 0,
+            _lib.current_stream(x.device)))
     if rc == _lib.ERR_UNSUPPORTED and x2 is not None:          # slab too large for the two-source kernel
         return groupnorm_silu_nhwc(torch.cat([x, x2], 1), norm, add_bc, res, want_sum, silu)
     _lib.check(rc, "bndm_groupnorm_nhwc_f32")
@@ -77,8 +90,9 @@ def add_bias_residual_nhwc(a, b, bias, bias_a=None, a2=None):
         b = b.contiguous(memory_format=torch.channels_last)
     out = torch.empty_like(a, memory_format=torch.channels_last)
     with torch.cuda.device(a.device):
-        rc = _lib.load().bndm_add_bias_nhwc_f32(_lib.ptr(a), _lib.ptr(a2), _lib.ptr(bias_a), _lib.ptr(b), _lib.ptr(bias),
-                                                _lib.ptr(out), a.numel(), a.shape[1], _lib.current_stream(a.device))
+        rc = _timed_launch("K6", 4 * a.numel() * (3 + (a2 is not None)), a.device, lambda: _lib.load().bndm_add_bias_nhwc_f32(
+            _lib.ptr(a), _lib.ptr(a2), _lib.ptr(bias_a), _lib.ptr(b), _lib.ptr(bias), _lib.ptr(out), a.numel(), a.shape[1],
+            _lib.current_stream(a.device)))
     _lib.check(rc, "bndm_add_bias_nhwc_f32")
     global LAUNCHES
     LAUNCHES += 1
@@ -91,7 +105,8 @@ def attention_small(qkv, C, head_dim=8):
     qkv = qkv.contiguous()
     out = torch.empty(B, T, C, dtype=torch.float32, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        rc = _lib.load().bndm_attention_small_f32(_lib.ptr(qkv), _lib.ptr(out), B, T, C, head_dim, _lib.current_stream(qkv.device))
+        rc = _timed_launch("K7", 4 * (qkv.numel() + out.numel()), qkv.device, lambda: _lib.load().bndm_attention_small_f32(
+            _lib.ptr(qkv), _lib.ptr(out), B, T, C, head_dim, _lib.current_stream(qkv.device)))
     _lib.check(rc, "bndm_attention_small_f32")
     global LAUNCHES
     LAUNCHES += 1

@@ -287,3 +287,19 @@ def test_sample_iadb_with_fused_unet_in_a_cuda_graph():
     assert torch.equal(eager, graphed)
     ref = osam.latent_loop(model, z, 5, "gaussianBN", 8)          # the oracle's loop around the same module
     np.testing.assert_allclose(graphed.cpu().numpy(), ref.cpu().numpy(), rtol=RTOL, atol=ATOL)
+
+
+def test_fused_unet_res128_matches_plain():
+    """cfg 4's UNet (7 blocks, 128x128): exercises the cluster-of-16 GroupNorm path."""
+    from bndm_b200.fused_unet import fuse_unet
+    from bndm_b200.unet import get_model
+    torch.manual_seed(1)
+    model = get_model(3, 6, 128).to(DEV).eval()
+    fused = fuse_unet(model)
+    x = torch.randn(2, 3, 128, 128, device=DEV)
+    t = torch.tensor([0.7, 0.1], device=DEV)
+    with torch.no_grad():
+        want = model(x, t, return_dict=False)[0]
+        got = fused(x, t, return_dict=False)[0]
+    scale = want.abs().max().item()
+    assert (got - want).abs().max().item() < 2e-2 * scale
