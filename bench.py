@@ -64,6 +64,17 @@ def parse_args():
     return p.parse_args()
 
 
+def ncu_traffic(key):
+    """DRAM bytes (read + write) per launch of a kernel from the committed ncu --set full capture
+    (profiles/traffic.json, written from the per-round ncu summaries), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(key, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -363,7 +374,7 @@ def run_ours(args):
     tf32_peak = pk["bf16_tflops"] / 2.0
     roofline = {"kernel": "gemm_tc_kernel (K1b: triangular L.z contraction, tcgen05 3xTF32)", "bound": "hbm",
                 "achieved": k1_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": k1_gbs / pk["hbm_gbs"],
-                "traffic": None, "peak_source": pk["source"] + " (burst copy bandwidth)",
+                "traffic": ncu_traffic("gemm_tc_kernel<96,0,1> B=64"), "peak_source": pk["source"] + " (burst copy bandwidth)",
                 "bytes_per_launch": k1_bytes, "ms_per_launch": gemm_ms, "launches_timed": len(k1_ms),
                 "pack_ms": statistics.mean(m[0] for m in k1_ms), "epilogue_ms": statistics.mean(m[2] for m in k1_ms),
                 "tensor": {"achieved_tflops_fp32_equiv": k1_flops / (gemm_ms * 1e-3) / 1e12,
@@ -371,7 +382,8 @@ def run_ours(args):
                            "peak_tf32_tflops": tf32_peak, "peak_note": "measured bf16 cuBLAS burst / 2",
                            "frac_issued": 3 * k1_flops / (gemm_ms * 1e-3) / 1e12 / tf32_peak}}
     roofline_step = {"kernel": "iadb_step_kernel (K2)", "bound": "hbm", "achieved": k2_gbs, "peak": pk["hbm_gbs"],
-                     "unit": "GB/s", "frac": k2_gbs / pk["hbm_gbs"], "traffic": None, "bytes_per_launch": k2_bytes,
+                     "unit": "GB/s", "frac": k2_gbs / pk["hbm_gbs"], "traffic": ncu_traffic("iadb_step_kernel B=64"),
+                     "bytes_per_launch": k2_bytes,
                      "ms_per_launch": k2_mean, "launches_timed": len(k2_ms),
                      "note": "d was written by the UNet's last conv just before: x/d are L2-resident, so this can "
                              "exceed the DRAM copy peak"}
