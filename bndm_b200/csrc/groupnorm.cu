@@ -45,8 +45,9 @@ __device__ __forceinline__ Moments merge(const Moments &a, const Moments &b) {
   const float d = b.mean - a.mean;
   Moments r;
   r.n = n;
-  r.mean = a.mean + d * (b.n / n);
-  r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / n);
+  const float f = __fdividef(b.n, n);             // SFU reciprocal: deterministic, ~2 ulp
+  r.mean = a.mean + d * f;
+  r.m2 = a.m2 + b.m2 + d * d * (a.n * f);
   return r;
 }
 
@@ -64,6 +65,37 @@ __device__ __forceinline__ void block_group_moments(Moments *s_part, Moments *s_
     Moments acc = s_part[tid * qpg];
     for (int t = 1; t < qpg; ++t) acc = merge(acc, s_part[tid * qpg + t]);
     s_out[tid] = acc;
+  }
+}
+
+// Same result layout, for q | 32 and nt % 32 == 0 (the common shapes): the lanes of a warp that share
+// a channel quad merge by shuffles (lower lane = left operand: fixed order, no barrier), one
+// __syncthreads publishes the per-warp partials, warp 0 finishes.  The barrier-heavy tree above was
+// the top stall of the kernel (ncu: 40 % of warp samples waiting at barriers).
+__device__ __forceinline__ void block_group_moments_shfl(Moments m, Moments *s_wpart, Moments *s_out, int tid, int nt, int q, int qpg,
+                                                         int n_groups) {
+  const int lane = tid & 31, warp = tid >> 5, n_warps = nt >> 5;
+  for (int off = q; off < 32; off <<= 1) {
+    Moments o;
+    o.n = __shfl_xor_sync(0xffffffffu, m.n, off);
+    o.mean = __shfl_xor_sync(0xffffffffu, m.mean, off);
+    o.m2 = __shfl_xor_sync(0xffffffffu, m.m2, off);
+    m = (lane & off) ? merge(o, m) : merge(m, o);
+  }
+  if (lane < q) s_wpart[warp * q + lane] = m;
+  __syncthreads();
+  if (warp == 0) {
+    if (lane < q) {
+      Moments acc = s_wpart[lane];
+      for (int w = 1; w < n_warps; ++w) acc = merge(acc, s_wpart[w * q + lane]);
+      s_wpart[lane] = acc;
+    }
+    __syncwarp();
+    if (lane < n_groups) {
+      Moments acc = s_wpart[lane * qpg];
+      for (int t = 1; t < qpg; ++t) acc = merge(acc, s_wpart[lane * qpg + t]);
+      s_out[lane] = acc;
+    }
   }
 }
 
@@ -189,94 +221,126 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
                : "memory");
 }
 
-__global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(GnArgs a, int P, int ppc) {
+// PERSISTENT: a cluster walks the work items (sample, channel block) item = cluster id + k * #clusters.
+// While a slab is normalised and stored, every quad a thread has consumed is immediately refilled
+// with the NEXT item's data by cp.async (same thread owns the same slab slots in every phase), so
+// the HBM reads of item i+1 overlap the writes of item i; without this all resident CTAs moved in
+// lock step (load, compute, store) and DRAM sat idle two thirds of the time (ncu: 33 %).
+__global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(GnArgs a, int P, int ppc, int n_items) {
   extern __shared__ __align__(16) float4 tile[];   // [pixels of this CTA][q] channel quads
   __shared__ Moments s_part[kGnMaxThreads];
-  __shared__ Moments s_grp[32];                     // this CTA's moments per group (read by the whole cluster)
+  __shared__ Moments s_grp[2][32];                  // this CTA's moments per group, double-buffered by item parity
   __shared__ float s_mean[32], s_rstd[32];
 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
-  const int b = blockIdx.y;
-  const int c0 = (blockIdx.x / P) * a.cblk;
+  const int cluster_id = blockIdx.x / P, n_clusters = gridDim.x / P;
+  const int n_cblk = a.C / a.cblk;
   const int q = a.cblk >> 2;
   const int tid = threadIdx.x, nt = blockDim.x;     // nt is a multiple of q
   const int px0 = rank * ppc;
   const int npx = max(0, min(ppc, a.HW - px0));
   const int n_quads = npx * q;
   const int rowq = a.C >> 2;
-
   // nt is a multiple of q: thread tid always handles quad cq = tid % q, pixels tid / q + k (nt / q)
   const int cq = tid % q;
   const int prow = tid / q, pstep = nt / q;
-  {
-    // the quad's channels live in x (row stride C1) or, for a concatenated input, in x2 (row stride C - C1)
+  const int g_local = (cq * 4) / a.cpg;
+  const int n_groups = a.cblk / a.cpg;
+
+  // source of this thread's quad for work item `item` (x, or x2 for the tail of a concatenated input)
+  auto src_of = [&](int item, const float4 *&src, size_t &step) {
+    const int b = item / n_cblk, c0 = (item - b * n_cblk) * a.cblk;
     const int cg0 = c0 + cq * 4;
     const bool second = a.x2 != nullptr && cg0 >= a.C1;
     const int srow = second ? a.C - a.C1 : a.C1;
     const float *sbase = second ? a.x2 + (cg0 - a.C1) : a.x + cg0;
-    const float4 *src = reinterpret_cast<const float4 *>(sbase + ((size_t)b * a.HW + px0 + prow) * srow);
-    const size_t step = (size_t)pstep * (srow >> 2);
+    src = reinterpret_cast<const float4 *>(sbase + ((size_t)b * a.HW + px0 + prow) * srow);
+    step = (size_t)pstep * (srow >> 2);
+  };
+
+  int item = cluster_id;
+  if (item < n_items) {
+    const float4 *src;
+    size_t step;
+    src_of(item, src, step);
     for (int i = tid; i < n_quads; i += nt, src += step) cp_async16(&tile[i], src);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 
-  const int c = c0 + cq * 4;
-  const int g_local = (cq * 4) / a.cpg;
-  const int n_groups = a.cblk / a.cpg;
-  float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (a.add_bc) add = __ldg(reinterpret_cast<const float4 *>(a.add_bc + (size_t)b * a.add_stride + c));
-  const float4 w = __ldg(reinterpret_cast<const float4 *>(a.weight + c));
-  const float4 bi = __ldg(reinterpret_cast<const float4 *>(a.bias + c));
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  for (int par = 0; item < n_items; item += n_clusters, par ^= 1) {
+    const int b = item / n_cblk, c0 = (item - b * n_cblk) * a.cblk;
+    const int c = c0 + cq * 4;
+    float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.add_bc) add = __ldg(reinterpret_cast<const float4 *>(a.add_bc + (size_t)b * a.add_stride + c));
+    const float4 w = __ldg(reinterpret_cast<const float4 *>(a.weight + c));
+    const float4 bi = __ldg(reinterpret_cast<const float4 *>(a.bias + c));
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
 
-  // ---- moments of this CTA's slab (s = x + add is written back so pass 2 reads s) --------------
-  float shift = 0.f, sum = 0.f, sq = 0.f, cnt = 0.f;
-  if (tid < n_quads) shift = tile[tid].x + add.x;
-  for (int i = tid; i < n_quads; i += nt) {
-    float4 s = tile[i];
-    s.x += add.x; s.y += add.y; s.z += add.z; s.w += add.w;
-    if (a.add_bc) tile[i] = s;
-    const float d0 = s.x - shift, d1 = s.y - shift, d2 = s.z - shift, d3 = s.w - shift;
-    sum += (d0 + d1) + (d2 + d3);
-    sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-    cnt += 4.f;
-  }
-  Moments m;
-  m.n = cnt;
-  m.mean = cnt > 0.f ? shift + sum / cnt : 0.f;
-  m.m2 = cnt > 0.f ? fmaxf(sq - sum * sum / cnt, 0.f) : 0.f;
-  s_part[tid] = m;
-  block_group_moments(s_part, s_grp, tid, nt, q, a.cpg >> 2, n_groups);
-  cluster.sync();                                   // every CTA's s_grp is complete and visible
-  if (tid < n_groups) {
-    Moments acc = {0.f, 0.f, 0.f};
-    for (int r = 0; r < P; ++r) {                   // rank order: every CTA computes the same bits
-      const Moments *remote = cluster.map_shared_rank(s_grp, r);
-      acc = merge(acc, remote[tid]);
+    // ---- moments of this CTA's slab (s = x + add is written back so the second pass reads s) -----
+    float shift = 0.f, sum = 0.f, sq = 0.f, cnt = 0.f;
+    if (tid < n_quads) shift = tile[tid].x + add.x;
+    for (int i = tid; i < n_quads; i += nt) {
+      float4 s = tile[i];
+      s.x += add.x; s.y += add.y; s.z += add.z; s.w += add.w;
+      if (a.add_bc) tile[i] = s;
+      const float d0 = s.x - shift, d1 = s.y - shift, d2 = s.z - shift, d3 = s.w - shift;
+      sum += (d0 + d1) + (d2 + d3);
+      sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      cnt += 4.f;
     }
-    s_mean[tid] = acc.mean;
-    s_rstd[tid] = rsqrtf(acc.m2 / acc.n + a.eps);
-  }
-  cluster.sync();                                   // nobody leaves (or reuses smem) while a peer still reads it
+    Moments m;
+    m.n = cnt;
+    m.mean = cnt > 0.f ? shift + sum / cnt : 0.f;
+    m.m2 = cnt > 0.f ? fmaxf(sq - sum * sum / cnt, 0.f) : 0.f;
+    if ((32 % q) == 0 && (nt & 31) == 0) {
+      block_group_moments_shfl(m, s_part, s_grp[par], tid, nt, q, a.cpg >> 2, n_groups);
+    } else {
+      s_part[tid] = m;
+      block_group_moments(s_part, s_grp[par], tid, nt, q, a.cpg >> 2, n_groups);
+    }
+    // One cluster barrier per item: s_grp is double-buffered, and a CTA can be at most one item ahead of
+    // a peer (it blocks at the next barrier), so nobody overwrites moments a peer still has to read.
+    cluster.sync();
+    if (tid < n_groups) {
+      Moments acc = {0.f, 0.f, 0.f};
+      for (int r = 0; r < P; ++r) {                 // rank order: every CTA computes the same bits
+        const Moments *remote = cluster.map_shared_rank(&s_grp[par][0], r);
+        acc = merge(acc, remote[tid]);
+      }
+      s_mean[tid] = acc.mean;
+      s_rstd[tid] = rsqrtf(acc.m2 / acc.n + a.eps);
+    }
+    __syncthreads();
 
-  // ---- normalise + affine + activation out of shared memory -----------------------------------
-  const float mean = s_mean[g_local], rstd = s_rstd[g_local];
-  const float4 sc = make_float4(rstd * w.x, rstd * w.y, rstd * w.z, rstd * w.w);
-  float4 *y4 = reinterpret_cast<float4 *>(a.y + ((size_t)b * a.HW + px0) * a.C + c0) + (size_t)prow * rowq + cq;
-  const size_t ystep = (size_t)pstep * rowq;
+    // ---- normalise + affine + activation out of shared memory; refill consumed slots with the next item ----
+    const float mean = s_mean[g_local], rstd = s_rstd[g_local];
+    const float4 sc = make_float4(rstd * w.x, rstd * w.y, rstd * w.z, rstd * w.w);
+    float4 *y4 = reinterpret_cast<float4 *>(a.y + ((size_t)b * a.HW + px0) * a.C + c0) + (size_t)prow * rowq + cq;
+    const size_t ystep = (size_t)pstep * rowq;
+    const int next = item + n_clusters;
+    const float4 *nsrc = nullptr;
+    size_t nstep = 0;
+    if (next < n_items) src_of(next, nsrc, nstep);
 #pragma unroll 4
-  for (int i = tid; i < n_quads; i += nt, y4 += ystep) {
-    const float4 s = tile[i];
-    float4 o;
-    o.x = (s.x - mean) * sc.x + bi.x;
-    o.y = (s.y - mean) * sc.y + bi.y;
-    o.z = (s.z - mean) * sc.z + bi.z;
-    o.w = (s.w - mean) * sc.w + bi.w;
-    if (a.silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-    *y4 = o;
+    for (int i = tid; i < n_quads; i += nt, y4 += ystep) {
+      const float4 s = tile[i];
+      if (nsrc) {
+        cp_async16(&tile[i], nsrc);
+        nsrc += nstep;
+      }
+      float4 o;
+      o.x = (s.x - mean) * sc.x + bi.x;
+      o.y = (s.y - mean) * sc.y + bi.y;
+      o.z = (s.z - mean) * sc.z + bi.z;
+      o.w = (s.w - mean) * sc.w + bi.w;
+      if (a.silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+      *y4 = o;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  cluster.sync();                                   // nobody leaves while a peer may still read its moments
 }
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
@@ -354,13 +418,10 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
       int rows = kGnMaxThreads / q;
       if (rows > ppc) rows = ppc;
       while (rows * q < 32) ++rows;
+      if (32 % q == 0) rows = (rows * q + 31) / 32 * 32 / q;      // whole warps: the shuffle merge needs them
       const int nt = rows * q;
-      if (P == 1) {            // a cluster of one: plain launch (this_cluster() degenerates to the CTA)
-        groupnorm_nhwc_cluster_kernel<<<dim3((unsigned)(C / cblk), (unsigned)B), nt, smem, s>>>(a, 1, ppc);
-        return cudaGetLastError();
-      }
+      const int n_items = B * (C / cblk);
       cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = dim3((unsigned)(P * (C / cblk)), (unsigned)B);
       cfg.blockDim = dim3((unsigned)nt);
       cfg.dynamicSmemBytes = smem;
       cfg.stream = s;
@@ -371,7 +432,22 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      return cudaLaunchKernelEx(&cfg, groupnorm_nhwc_cluster_kernel, a, P, ppc);
+      // persistent grid: as many clusters as can be resident at once (cached per launch shape)
+      static int cache_key[3] = {0, 0, 0}, cache_val = 0;
+      int max_clusters = 0;
+      if (cache_key[0] == P && cache_key[1] == nt && cache_key[2] == (int)smem) {
+        max_clusters = cache_val;
+      } else {
+        cfg.gridDim = dim3((unsigned)P, 1, 1);
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, groupnorm_nhwc_cluster_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+          cudaGetLastError();
+          max_clusters = 148 / P > 0 ? 148 / P : 1;
+        }
+        cache_key[0] = P; cache_key[1] = nt; cache_key[2] = (int)smem; cache_val = max_clusters;
+      }
+      const int n_clusters = n_items < max_clusters ? n_items : max_clusters;
+      cfg.gridDim = dim3((unsigned)(P * n_clusters), 1, 1);
+      return cudaLaunchKernelEx(&cfg, groupnorm_nhwc_cluster_kernel, a, P, ppc, n_items);
     }
   }
   if (x2) return cudaErrorInvalidValue;                           // slab does not fit: caller concatenates first
