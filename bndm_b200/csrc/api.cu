@@ -538,7 +538,10 @@ int bndm_groupnorm_nhwc_f32(const float *x, const float *x2, int C1, const float
     set_error("groupnorm: bad second source (C1=%d of C=%d)", C1, C);
     return BNDM_ERR_ARG;
   }
-  if (add_bc && (add_bc_stride < C || add_bc_stride % 4 != 0)) { set_error("groupnorm: bad add_bc stride"); return BNDM_ERR_ARG; }
+  if (add_bc && ((add_bc_stride != 0 && add_bc_stride < C) || add_bc_stride % 4 != 0)) {     // 0 = one row for all samples
+    set_error("groupnorm: bad add_bc stride");
+    return BNDM_ERR_ARG;
+  }
   if (!x || !weight || !bias || !y || B < 1 || C < 1 || HW < 1 || groups < 1) { set_error("groupnorm: bad argument"); return BNDM_ERR_ARG; }
   if (C % groups != 0 || (C / groups) % 4 != 0) {
     set_error("groupnorm: channels per group must be a multiple of 4 (C=%d, groups=%d)", C, groups);

@@ -226,6 +226,8 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 // with the NEXT item's data by cp.async (same thread owns the same slab slots in every phase), so
 // the HBM reads of item i+1 overlap the writes of item i; without this all resident CTAs moved in
 // lock step (load, compute, store) and DRAM sat idle two thirds of the time (ncu: 33 %).
+// kCluster = false: P == 1 (small activations), launched without a cluster; block barriers only.
+template <bool kCluster>
 __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(GnArgs a, int P, int ppc, int n_items) {
   extern __shared__ __align__(16) float4 tile[];   // [pixels of this CTA][q] channel quads
   __shared__ Moments s_part[kGnMaxThreads];
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
   __shared__ float s_mean[32], s_rstd[32];
 
   cg::cluster_group cluster = cg::this_cluster();
-  const int rank = (int)cluster.block_rank();
+  const int rank = kCluster ? (int)cluster.block_rank() : 0;
   const int cluster_id = blockIdx.x / P, n_clusters = gridDim.x / P;
   const int n_cblk = a.C / a.cblk;
   const int q = a.cblk >> 2;
@@ -302,12 +304,16 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
     }
     // One cluster barrier per item: s_grp is double-buffered, and a CTA can be at most one item ahead of
     // a peer (it blocks at the next barrier), so nobody overwrites moments a peer still has to read.
-    cluster.sync();
+    if (kCluster) cluster.sync(); else __syncthreads();
     if (tid < n_groups) {
       Moments acc = {0.f, 0.f, 0.f};
-      for (int r = 0; r < P; ++r) {                 // rank order: every CTA computes the same bits
-        const Moments *remote = cluster.map_shared_rank(&s_grp[par][0], r);
-        acc = merge(acc, remote[tid]);
+      if (kCluster) {
+        for (int r = 0; r < P; ++r) {               // rank order: every CTA computes the same bits
+          const Moments *remote = cluster.map_shared_rank(&s_grp[par][0], r);
+          acc = merge(acc, remote[tid]);
+        }
+      } else {
+        acc = s_grp[par][tid];
       }
       s_mean[tid] = acc.mean;
       s_rstd[tid] = rsqrtf(acc.m2 / acc.n + a.eps);
@@ -340,7 +346,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  cluster.sync();                                   // nobody leaves while a peer may still read its moments
+  if (kCluster) cluster.sync();                     // nobody leaves while a peer may still read its moments
 }
 
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
@@ -411,8 +417,9 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
     const int ppc = (HW + P - 1) / P;
     const size_t smem = (size_t)ppc * row_bytes;
     if (smem <= 200 * 1024) {
-      cudaError_t e = cudaFuncSetAttribute(groupnorm_nhwc_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      if (e == cudaSuccess && P > 8) e = cudaFuncSetAttribute(groupnorm_nhwc_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      cudaError_t e = cudaFuncSetAttribute(groupnorm_nhwc_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(groupnorm_nhwc_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (e == cudaSuccess && P > 8) e = cudaFuncSetAttribute(groupnorm_nhwc_cluster_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
       if (e != cudaSuccess) return e;
       // small slabs: no more thread rows than pixels (shallower merge tree, cheaper CTAs)
       int rows = kGnMaxThreads / q;
@@ -421,6 +428,17 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
       if (32 % q == 0) rows = (rows * q + 31) / 32 * 32 / q;      // whole warps: the shuffle merge needs them
       const int nt = rows * q;
       const int n_items = B * (C / cblk);
+      if (P == 1) {
+        // small activations: no cluster; persistent over min(items, resident CTAs)
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, groupnorm_nhwc_cluster_kernel<false>, nt, smem) != cudaSuccess || per_sm < 1) {
+          cudaGetLastError();
+          per_sm = 1;
+        }
+        const int resident = per_sm * 148;
+        groupnorm_nhwc_cluster_kernel<false><<<n_items < resident ? n_items : resident, nt, smem, s>>>(a, 1, ppc, n_items);
+        return cudaGetLastError();
+      }
       cudaLaunchConfig_t cfg = {};
       cfg.blockDim = dim3((unsigned)nt);
       cfg.dynamicSmemBytes = smem;
@@ -439,7 +457,7 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
         max_clusters = cache_val;
       } else {
         cfg.gridDim = dim3((unsigned)P, 1, 1);
-        if (cudaOccupancyMaxActiveClusters(&max_clusters, groupnorm_nhwc_cluster_kernel, &cfg) != cudaSuccess || max_clusters < 1) {
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, groupnorm_nhwc_cluster_kernel<true>, &cfg) != cudaSuccess || max_clusters < 1) {
           cudaGetLastError();
           max_clusters = 148 / P > 0 ? 148 / P : 1;
         }
@@ -447,7 +465,7 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
       }
       const int n_clusters = n_items < max_clusters ? n_items : max_clusters;
       cfg.gridDim = dim3((unsigned)(P * n_clusters), 1, 1);
-      return cudaLaunchKernelEx(&cfg, groupnorm_nhwc_cluster_kernel, a, P, ppc, n_items);
+      return cudaLaunchKernelEx(&cfg, groupnorm_nhwc_cluster_kernel<true>, a, P, ppc, n_items);
     }
   }
   if (x2) return cudaErrorInvalidValue;                           // slab does not fit: caller concatenates first

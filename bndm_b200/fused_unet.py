@@ -64,6 +64,8 @@ def groupnorm_silu_nhwc(x, norm, add_bc=None, res=None, want_sum=False, silu=Tru
     s = torch.empty_like(y) if want_sum else None
     stride = 0
     if add_bc is not None:
+        if add_bc.dim() == 1:                                                          # per-channel bias: one row for all samples
+            add_bc = add_bc[None, :].expand(B, C)
         if add_bc.dim() != 2 or add_bc.shape != (B, C) or add_bc.stride(1) != 1:      # a column slice is fine
             add_bc = add_bc.reshape(B, C).contiguous()
         stride = add_bc.stride(0)
@@ -137,6 +139,7 @@ class FusedUNet2D(torch.nn.Module):
             off += n
 
         self._sc_w = {}
+        self._pend = {}
         self._qkv = {}
         for mod in self.m.modules():
             if mod.__class__.__name__ == "Attention":
@@ -154,22 +157,41 @@ class FusedUNet2D(torch.nn.Module):
         return out
 
     # -- blocks ---------------------------------------------------------------------------------
-    def _resnet(self, blk, x, tb_all, x2=None):
+    def _resnet(self, blk, x, tb_all, x2=None, x_bias=None, x2_bias=None):
         """x2: the block's input is cat((x, x2), 1) (up blocks) -- never materialised: norm1 reads both
-        tensors and the 1x1 conv_shortcut is applied to the two halves separately."""
+        tensors and the 1x1 conv_shortcut is applied to the two halves separately.
+        x_bias / x2_bias: per-channel biases still owed to x / x2 (the producing convolution ran without
+        its bias): norm1 adds them on the fly and the shortcut absorbs them into its own bias."""
         lo, hi = self._temb_slices[id(blk)]
-        y = groupnorm_silu_nhwc(x, blk.norm1, x2=x2)
+        pend = self._pending(blk, x.shape[1], x_bias, x2.shape[1] if x2 is not None else 0, x2_bias)
+        y = groupnorm_silu_nhwc(x, blk.norm1, x2=x2, add_bc=pend["norm_add"])
         h = F.conv2d(y, blk.conv1.weight, None, padding=1)                 # bias folded into tb_all
         y2 = groupnorm_silu_nhwc(h, blk.norm2, add_bc=tb_all[:, lo:hi])
         h2 = F.conv2d(y2, blk.conv2.weight, None, padding=1)               # bias added with the residual (K6)
         if x2 is not None:
             w1, w2 = self._sc_split(blk, x.shape[1])
             sc, sc2 = F.conv2d(x, w1, None), F.conv2d(x2, w2, None)
-            return add_bias_residual_nhwc(sc, h2, blk.conv2.bias, bias_a=blk.conv_shortcut.bias, a2=sc2)
+            return add_bias_residual_nhwc(sc, h2, blk.conv2.bias, bias_a=pend["sc_bias"], a2=sc2)
         if blk.conv_shortcut is not None:
             sc = F.conv2d(x, blk.conv_shortcut.weight, None)              # 1x1; its bias is added in K6 too
-            return add_bias_residual_nhwc(sc, h2, blk.conv2.bias, bias_a=blk.conv_shortcut.bias)
-        return add_bias_residual_nhwc(x, h2, blk.conv2.bias)
+            return add_bias_residual_nhwc(sc, h2, blk.conv2.bias, bias_a=pend["sc_bias"])
+        return add_bias_residual_nhwc(x, h2, blk.conv2.bias, bias_a=x_bias)
+
+    def _pending(self, blk, c1, x_bias, c2, x2_bias):
+        """Cached per block: the (C,) vector norm1 must add and the shortcut's effective bias."""
+        key = id(blk)
+        if key not in self._pend:
+            norm_add, sc_bias = None, (blk.conv_shortcut.bias if blk.conv_shortcut is not None else None)
+            if x_bias is not None or x2_bias is not None:
+                dev = blk.norm1.weight.device
+                parts = [x_bias if x_bias is not None else torch.zeros(c1, device=dev)]
+                if c2:
+                    parts.append(x2_bias if x2_bias is not None else torch.zeros(c2, device=dev))
+                norm_add = torch.cat(parts).contiguous()
+                if blk.conv_shortcut is not None:                         # W (x + b) = W x + W b
+                    sc_bias = blk.conv_shortcut.bias + blk.conv_shortcut.weight[:, :, 0, 0] @ norm_add
+            self._pend[key] = {"norm_add": norm_add, "sc_bias": sc_bias}
+        return self._pend[key]
 
     def _sc_split(self, blk, c1):
         key = (id(blk), c1)
@@ -199,26 +221,31 @@ class FusedUNet2D(torch.nn.Module):
         o = o.reshape(B, H, W, C).permute(0, 3, 1, 2)                      # channels-last view
         return add_bias_residual_nhwc(x, o, att.to_out[0].bias)
 
-    def _down(self, block, h, temb_act):
+    def _down(self, block, h, temb_act, h_bias=None):
         skips = []
         for i, resnet in enumerate(block.resnets):
-            h = self._resnet(resnet, h, temb_act)
+            h = self._resnet(resnet, h, temb_act, x_bias=h_bias if i == 0 else None)
             if block.attentions is not None:
                 h = self._attention(block.attentions[i], h)
-            skips.append(h)
+            skips.append((h, None))
         if block.downsamplers is not None:
             h = block.downsamplers[0](h)
-            skips.append(h)
+            skips.append((h, None))
         return h, skips
 
-    def _up(self, block, h, skips, temb_act):
+    def _up(self, block, h, skips, temb_act, h_bias=None):
+        """Returns (h, bias still owed to h): the upsampler's convolution runs without its bias, the next
+        block's first resnet absorbs it (saves a full read+write of the upsampled activation)."""
         for i, resnet in enumerate(block.resnets):
-            h = self._resnet(resnet, h, temb_act, x2=skips.pop())
+            skip, skip_bias = skips.pop()
+            h = self._resnet(resnet, h, temb_act, x2=skip, x_bias=h_bias if i == 0 else None, x2_bias=skip_bias)
             if block.attentions is not None:
                 h = self._attention(block.attentions[i], h)
         if block.upsamplers is not None:
-            h = block.upsamplers[0](h)
-        return h
+            conv = block.upsamplers[0].conv
+            h = F.conv2d(F.interpolate(h, scale_factor=2.0, mode="nearest"), conv.weight, None, padding=1)
+            return h, conv.bias
+        return h, None
 
     kernels_per_forward = None      # K5 + K6 launches of one forward (set by the first call)
 
@@ -236,17 +263,19 @@ class FusedUNet2D(torch.nn.Module):
         temb_act = F.silu(m.time_embedding(emb))
         temb_act = torch.addmm(self.temb_b, temb_act, self.temb_w.t())      # (B, sum of Cout): all projections
 
-        h = m.conv_in(sample.float().contiguous(memory_format=torch.channels_last))
-        skips = [h]
-        for block in m.down_blocks:
-            h, s = self._down(block, h, temb_act)
+        # conv_in's bias is owed to h: the first resnet and the last skip consumer absorb it
+        h = F.conv2d(sample.float().contiguous(memory_format=torch.channels_last), m.conv_in.weight, None, padding=1)
+        skips = [(h, m.conv_in.bias)]
+        for i, block in enumerate(m.down_blocks):
+            h, s = self._down(block, h, temb_act, h_bias=m.conv_in.bias if i == 0 else None)
             skips.extend(s)
         h = self._resnet(m.mid_block.resnets[0], h, temb_act)
         h = self._attention(m.mid_block.attentions[0], h)
         h = self._resnet(m.mid_block.resnets[1], h, temb_act)
+        owed = None
         for block in m.up_blocks:
-            h = self._up(block, h, skips, temb_act)
-        h = m.conv_out(groupnorm_silu_nhwc(h, m.conv_norm_out))
+            h, owed = self._up(block, h, skips, temb_act, h_bias=owed)
+        h = m.conv_out(groupnorm_silu_nhwc(h, m.conv_norm_out, add_bc=owed))
         h = h.contiguous()                                   # NCHW for the step kernels
         if self.kernels_per_forward is None:
             self.kernels_per_forward = LAUNCHES - launches_before

@@ -155,7 +155,8 @@ int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_s
  *      res and sum_out must then be NULL)
  *     y = act((s - mean_group) * rstd_group * weight[c] + bias[c]),  act = SiLU iff apply_silu
  * x, res, sum_out, y: dev, NHWC [B][HW][C] fp32; add_bc: dev, B rows of C floats `add_bc_stride`
- * floats apart (a column slice of a wider matrix), or NULL; weight, bias: dev [C].
+ * floats apart (a column slice of a wider matrix; 0 = the same row for every sample, i.e. a
+ * per-channel bias), or NULL; weight, bias: dev [C].
  * groups as torch.nn.GroupNorm (biased variance, eps inside the sqrt); C/groups % 4 == 0.
  * Replaces RowwiseMoments + affine + SiLU (+ broadcast / residual add) kernels of PyTorch.     */
 int bndm_groupnorm_nhwc_f32(const float *x, const float *x2, int C1, const float *res, const float *add_bc,
