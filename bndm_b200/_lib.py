@@ -35,6 +35,7 @@ SIGNATURES = {
     "bndm_white128_reinterpret_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "bndm_iadb_step_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_iadb_step_sched_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "bndm_iadb_step_sched_dnhwc_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_ddim_step_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int64, _P]),
     "bndm_debug_set_trace": (C.c_int, [_P, _P]),
     "bndm_debug_set_policy": (C.c_int, [C.c_int, C.c_int]),
@@ -42,6 +43,7 @@ SIGNATURES = {
     "bndm_debug_streamk_check_sub": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "bndm_groupnorm_nhwc_f32": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_float, C.c_int, _P]),
+    "bndm_upsample2x_nhwc_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_attention_small_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_add_bias_nhwc_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
     "bndm_to_uint8_nhwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

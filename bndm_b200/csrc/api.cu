@@ -430,19 +430,29 @@ int bndm_iadb_step_f32(float *x_out, const float *x, const float *d, const float
   int rc = check_step(x_out, x, d, B, C, HW, d_channels);
   if (rc != BNDM_OK) return rc;
   if (!dalpha || (d_channels == 2 * C && !dgamma)) { set_error("iadb step: missing coefficient vector"); return BNDM_ERR_ARG; }
-  IadbArgs a{x_out, x, d, dalpha, dgamma, nullptr, nullptr, nullptr, B, C, HW, d_channels};
+  IadbArgs a{x_out, x, d, dalpha, dgamma, nullptr, nullptr, nullptr, B, C, HW, d_channels, 0};
   CK(launch_iadb_step(a, false, (cudaStream_t)stream));
+  return BNDM_OK;
+}
+
+static int iadb_sched(float *x_out, const float *x, const float *d, const float *table, int *state, float *t_next_out, int B,
+                      int C, int HW, int d_channels, int d_nhwc, void *stream) {
+  int rc = check_step(x_out, x, d, B, C, HW, d_channels);
+  if (rc != BNDM_OK) return rc;
+  if (!table || !state) { set_error("iadb sched step: null table/state"); return BNDM_ERR_ARG; }
+  IadbArgs a{x_out, x, d, nullptr, nullptr, table, state, t_next_out, B, C, HW, d_channels, d_nhwc};
+  CK(launch_iadb_step(a, true, (cudaStream_t)stream));
   return BNDM_OK;
 }
 
 int bndm_iadb_step_sched_f32(float *x_out, const float *x, const float *d, const float *table, int *state,
                              float *t_next_out, int B, int C, int HW, int d_channels, void *stream) {
-  int rc = check_step(x_out, x, d, B, C, HW, d_channels);
-  if (rc != BNDM_OK) return rc;
-  if (!table || !state) { set_error("iadb sched step: null table/state"); return BNDM_ERR_ARG; }
-  IadbArgs a{x_out, x, d, nullptr, nullptr, table, state, t_next_out, B, C, HW, d_channels};
-  CK(launch_iadb_step(a, true, (cudaStream_t)stream));
-  return BNDM_OK;
+  return iadb_sched(x_out, x, d, table, state, t_next_out, B, C, HW, d_channels, 0, stream);
+}
+
+int bndm_iadb_step_sched_dnhwc_f32(float *x_out, const float *x, const float *d_nhwc, const float *table, int *state,
+                                   float *t_next_out, int B, int C, int HW, int d_channels, void *stream) {
+  return iadb_sched(x_out, x, d_nhwc, table, state, t_next_out, B, C, HW, d_channels, 1, stream);
 }
 
 int bndm_ddim_step_f32(float *x_out, const float *x, const float *eps, const float *noise, const float *coef, int *state,
@@ -505,6 +515,13 @@ int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_s
   delete[] owner;
   delete[] tile_of;
   return rc;
+}
+
+int bndm_upsample2x_nhwc_f32(const float *x, float *y, int B, int H, int W, int C, void *stream) {
+  if (!x || !y || B < 1 || H < 1 || W < 1 || C < 4 || C % 4 != 0) { set_error("upsample2x: bad argument"); return BNDM_ERR_ARG; }
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) % 16 != 0) { set_error("upsample2x: misaligned"); return BNDM_ERR_ARG; }
+  CK(launch_upsample2x_nhwc(x, y, B, H, W, C, (cudaStream_t)stream));
+  return BNDM_OK;
 }
 
 int bndm_attention_small_f32(const float *qkv, float *out, int B, int T, int C, int head_dim, void *stream) {

@@ -213,6 +213,7 @@ struct IadbArgs {
   int *state;                     // {step_idx, blocks_done}              (scheduled mode)
   float *t_next_out;              // [B] or null
   int B, C, HW, Cd;
+  int d_nhwc;                     // d is channels-last [B][HW][Cd] (the fused UNet's native output) instead of NCHW
 };
 
 cudaError_t launch_iadb_step(const IadbArgs &a, bool sched, cudaStream_t s);
@@ -228,6 +229,7 @@ struct DdimArgs {
 };
 
 cudaError_t launch_ddim_step(const DdimArgs &a, cudaStream_t s);
+cudaError_t launch_upsample2x_nhwc(const float *x, float *y, int B, int H, int W, int C, cudaStream_t s);
 cudaError_t launch_attention_small(const float *qkv, float *out, int B, int T, int C, int head_dim, cudaStream_t s);
 cudaError_t launch_add_bias_nhwc(const float *a, const float *a2, const float *bias_a, const float *b, const float *bias_b,
                                  float *out, size_t n, int C, cudaStream_t s);

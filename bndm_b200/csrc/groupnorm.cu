@@ -547,3 +547,38 @@ cudaError_t launch_attention_small(const float *qkv, float *out, int B, int T, i
 }
 
 }  // namespace bndm
+
+// K8: nearest-neighbour 2x upsampling of a channels-last activation (diffusers Upsample2D in front of its
+// 3x3 convolution): y[b][2i+a][2j+c][:] = x[b][i][j][:].  One thread per input channel quad: one 16-byte
+// load, four 16-byte stores, all coalesced (PyTorch's upsample_nearest2d_nhwc kernel moves the same bytes
+// at under 1 TB/s).
+namespace bndm {
+
+__global__ void __launch_bounds__(256) upsample2x_nhwc_kernel(const float4 *__restrict__ x, float4 *__restrict__ y, int H, int W,
+                                                              int cq, size_t n_in) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += stride) {
+    const size_t pix = i / cq;                    // ((b * H + h) * W + w)
+    const int c = (int)(i - pix * cq);
+    const int w = (int)(pix % W);
+    const size_t bh = pix / W;                    // b * H + h
+    const float4 v = __ldg(x + i);
+    float4 *o = y + ((bh * 2) * (size_t)(2 * W) + 2 * w) * cq + c;      // output row 2h of image b (2H rows per image)
+    o[0] = v;
+    o[cq] = v;
+    o += (size_t)(2 * W) * cq;
+    o[0] = v;
+    o[cq] = v;
+  }
+}
+
+cudaError_t launch_upsample2x_nhwc(const float *x, float *y, int B, int H, int W, int C, cudaStream_t s) {
+  const size_t n_in = (size_t)B * H * W * (C / 4);
+  size_t blocks = (n_in + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_nhwc_kernel<<<(unsigned)blocks, 256, 0, s>>>(reinterpret_cast<const float4 *>(x), reinterpret_cast<float4 *>(y), H, W,
+                                                          C / 4, n_in);
+  return cudaGetLastError();
+}
+
+}  // namespace bndm

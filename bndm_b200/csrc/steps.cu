@@ -65,7 +65,20 @@ __global__ void __launch_bounds__(256, kStepBlocksPerSM) iadb_step_kernel(IadbAr
     b = (int)(bc / a.C);
     xo = (int64_t)bc * a.HW + hw;
     const int64_t d1 = xo + (int64_t)b * (a.Cd - a.C) * a.HW;       // ((b Cd + c) HW + hw)
-    if (kVec) {
+    if (a.d_nhwc) {
+      // channels-last UNet output d[b][hw][Cd]: channel c (and c + C) of V consecutive pixels
+      const int c = (int)(bc - (unsigned)b * a.C);
+      const float *dp = a.d + ((int64_t)b * a.HW + hw) * a.Cd + c;
+      u.x = __ldg(dp);
+      if (two) v.x = __ldg(dp + a.C);
+      if (kVec) {
+        u.y = __ldg(dp + a.Cd); u.z = __ldg(dp + 2 * a.Cd); u.w = __ldg(dp + 3 * a.Cd);
+        if (two) { v.y = __ldg(dp + a.Cd + a.C); v.z = __ldg(dp + 2 * a.Cd + a.C); v.w = __ldg(dp + 3 * a.Cd + a.C); }
+        xv = *reinterpret_cast<const float4 *>(a.x + xo);
+      } else {
+        xv.x = a.x[xo];
+      }
+    } else if (kVec) {
       xv = *reinterpret_cast<const float4 *>(a.x + xo);
       u = ldg4(a.d + d1);
       if (two) v = ldg4(a.d + d1 + plane);

@@ -101,6 +101,21 @@ def add_bias_residual_nhwc(a, b, bias, bias_a=None, a2=None):
     return out
 
 
+def upsample2x_nhwc(x):
+    """F.interpolate(x, scale_factor=2, mode="nearest") for a channels-last (B,C,H,W) tensor (K8)."""
+    B, C, H, W = x.shape
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    y = torch.empty((B, C, 2 * H, 2 * W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        rc = _timed_launch("K8", 4 * (x.numel() + y.numel()), x.device, lambda: _lib.load().bndm_upsample2x_nhwc_f32(
+            _lib.ptr(x), _lib.ptr(y), B, H, W, C, _lib.current_stream(x.device)))
+    _lib.check(rc, "bndm_upsample2x_nhwc_f32")
+    global LAUNCHES
+    LAUNCHES += 1
+    return y
+
+
 def attention_small(qkv, C, head_dim=8):
     """softmax(q k^T / sqrt(d)) v for (B, T, 3C) packed projections with tiny T (K7)."""
     B, T, _ = qkv.shape
@@ -243,7 +258,7 @@ class FusedUNet2D(torch.nn.Module):
                 h = self._attention(block.attentions[i], h)
         if block.upsamplers is not None:
             conv = block.upsamplers[0].conv
-            h = F.conv2d(F.interpolate(h, scale_factor=2.0, mode="nearest"), conv.weight, None, padding=1)
+            h = F.conv2d(upsample2x_nhwc(h), conv.weight, None, padding=1)
             return h, conv.bias
         return h, None
 
@@ -276,7 +291,8 @@ class FusedUNet2D(torch.nn.Module):
         for block in m.up_blocks:
             h, owed = self._up(block, h, skips, temb_act, h_bias=owed)
         h = m.conv_out(groupnorm_silu_nhwc(h, m.conv_norm_out, add_bc=owed))
-        h = h.contiguous()                                   # NCHW for the step kernels
+        # left in channels-last memory: K2 (bndm_iadb_step_sched_dnhwc_f32) consumes it in place; any
+        # other consumer sees an ordinary (B, C, H, W) tensor
         if self.kernels_per_forward is None:
             self.kernels_per_forward = LAUNCHES - launches_before
         if not return_dict:

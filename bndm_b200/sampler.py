@@ -67,11 +67,16 @@ class IadbStepper:
     def step_(self, x: torch.Tensor, d: torch.Tensor):
         """x <- x + dalpha*d[:, :C] (+ dgamma*d[:, C:]) in place; advances t_vec / state."""
         B, C = x.shape[0], x.shape[1]
-        d = _lib.require_cuda_f32(d, "model output")
+        lib = _lib.load()
+        # the channels-last UNet evaluation hands over d in NHWC memory: consumed in place
+        nhwc = (isinstance(d, torch.Tensor) and d.is_cuda and d.dtype == torch.float32 and d.dim() == 4 and not d.is_contiguous()
+                and d.is_contiguous(memory_format=torch.channels_last))
+        if not nhwc:
+            d = _lib.require_cuda_f32(d, "model output")
+        fn = lib.bndm_iadb_step_sched_dnhwc_f32 if nhwc else lib.bndm_iadb_step_sched_f32
         with torch.cuda.device(self.device):
-            rc = _lib.load().bndm_iadb_step_sched_f32(
-                _lib.ptr(x), _lib.ptr(x), _lib.ptr(d), _lib.ptr(self.table), _lib.ptr(self.state),
-                _lib.ptr(self.t_vec), B, C, x.shape[2] * x.shape[3], d.shape[1], _lib.current_stream(self.device))
+            rc = fn(_lib.ptr(x), _lib.ptr(x), _lib.ptr(d), _lib.ptr(self.table), _lib.ptr(self.state),
+                    _lib.ptr(self.t_vec), B, C, x.shape[2] * x.shape[3], d.shape[1], _lib.current_stream(self.device))
         _lib.check(rc, "bndm_iadb_step_sched_f32")
         return x
 
@@ -119,7 +124,7 @@ class GraphedStep:
         x_static.copy_(keep)
         stepper.reset()
         with torch.cuda.graph(self.graph, stream=side):
-            d = _lib.require_cuda_f32(model_call(x_static, stepper.t_vec), "model output")
+            d = model_call(x_static, stepper.t_vec)
             if fused:
                 stepper.step_(x_static, d)
             else:

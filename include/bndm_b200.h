@@ -116,6 +116,11 @@ int bndm_iadb_step_f32(float *x_out, const float *x, const float *d, const float
 int bndm_iadb_step_sched_f32(float *x_out, const float *x, const float *d, const float *table,
                              int *state, float *t_next_out, int B, int C, int HW, int d_channels,
                              void *stream);
+/* Same, with the UNet output in channels-last memory (d_nhwc: [B][HW][d_channels]) -- what the
+ * channels-last UNet evaluation produces natively, consumed in place (no NCHW copy); x stays NCHW. */
+int bndm_iadb_step_sched_dnhwc_f32(float *x_out, const float *x, const float *d_nhwc, const float *table,
+                                   int *state, float *t_next_out, int B, int C, int HW, int d_channels,
+                                   void *stream);
 
 /* DDIM update, epsilon prediction (diffusers DDIMScheduler.step as called at
  * ddim_diffusers.py:680; parity unpinned, see oracle/sampler.py):
@@ -162,6 +167,10 @@ int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_s
 int bndm_groupnorm_nhwc_f32(const float *x, const float *x2, int C1, const float *res, const float *add_bc,
                             int add_bc_stride, const float *weight, const float *bias, float *sum_out, float *y, int B,
                             int C, int HW, int groups, float eps, int apply_silu, void *stream);
+
+/* K8 -- nearest-neighbour 2x upsampling of an NHWC fp32 activation: x dev [B][H][W][C] -> y dev
+ * [B][2H][2W][C] (diffusers Upsample2D's F.interpolate(scale_factor=2, mode="nearest")).  C % 4 == 0. */
+int bndm_upsample2x_nhwc_f32(const float *x, float *y, int B, int H, int W, int C, void *stream);
 
 /* K7 -- softmax(q k^T / sqrt(head_dim)) v for the UNet's attention blocks at their tiny sizes (4x4 / 2x2
  * resolution, head_dim 8): qkv dev [B][T][3C] (q | k | v on the last axis, head h = channels 8h..8h+7),
