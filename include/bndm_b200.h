@@ -127,8 +127,9 @@ int bndm_iadb_step_sched_dnhwc_f32(float *x_out, const float *x, const float *d_
  *     x0  = clamp((x - c[1]*eps) / c[0], -1, 1)          (clamp iff clip != 0)
  *     out = (c[2]*x0 + c[3]*eps) [+ c[4]*noise]          (noise may be NULL => eta = 0)
  * coef: dev, rows of 8 floats {sqrt(abar_t), sqrt(1-abar_t), sqrt(abar_prev),
- * sqrt(1-abar_prev-sigma^2), sigma, t_next, 0, 0}; row *state (state == NULL => row 0, no
- * increment).  t_next_out: dev [B] float or NULL.  n = B*C*H*W.  x_out may alias x.        */
+ * sqrt(1-abar_prev-sigma^2), sigma, t_next, 0, 0}; the row used is ticket / gridDim like the
+ * scheduled IADB step (state[0] = run-long block-ticket counter, zero before the first step;
+ * state == NULL => row 0).  t_next_out: dev [B] float or NULL.  n = B*C*H*W.  x_out may alias x. */
 int bndm_ddim_step_f32(float *x_out, const float *x, const float *eps, const float *noise,
                        const float *coef, int *state, float *t_next_out, int B, int clip, int64_t n,
                        void *stream);
