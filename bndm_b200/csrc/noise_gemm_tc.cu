@@ -1,39 +1,46 @@
 // K1b (tensor-core variant): the triangular contraction  bn[j][p] = sum_k L[p][k] * z[j][k]
-// on tcgen05 with bulk-copy (TMA) staged operands and TMEM accumulators.  sm_100a only.
+// on tcgen05 with TMA-staged operands and TMEM accumulators.  sm_100a only.
 //
-// OPERAND LAYOUT (built once per L by tile_L_kernel, per call for z by pack_kernel; see
-// noise_pack.cu).  A "stage" is one 128-row tile of L x 32 k values.  Both operands live in
-// global memory as a sequence of stage blocks that already have the shared-memory image the
-// tensor core wants (K-major, 128-byte rows, SWIZZLE_128B: 16-byte chunk c of row r sits at
-// chunk c ^ (r & 7) of its 8-row / 1024-byte group), so ONE linear cp.async.bulk per operand
-// per stage brings a block in -- no tensor maps, every DRAM burst a full 32 KiB / 2 nb * 128 B:
-//     L block (tile i, stage s)  = [ Lh tile 16 KiB | Ll tile 16 KiB ]          at Lt + 32 KiB * (cum(i) + s)
-//     z block (col block cb, s)  = [ zh rows 0..nb-1 | zl rows nb..2nb-1 ]      at zt + 256 nb B * (128 cb + s)
-// Only the blocks a lower-triangular L needs exist: row tile i has 4 (i + 1) of them.
+// OPERAND LAYOUT.  A "k-stage" is one 128-row tile of L x 32 k values.  L lives in global memory
+// as a sequence of stage blocks that already have the shared-memory image the tensor core wants
+// (K-major, 128-byte rows, SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7) of
+// its 8-row / 1024-byte group), so ONE linear cp.async.bulk brings a block (or two adjacent
+// ones) in -- no tensor map, full-burst DRAM reads.  Only the blocks a lower-triangular L needs
+// exist: row tile i has 4 (i + 1) of them, starting at block 2 i (i + 1).  Two variants:
+//   pre-split (kRawL = false)  L block = [ Lh tile | Ll tile ] (32 KiB, hi rounded to nearest);
+//                              z block (col block cb, k-stage s) = [ zh rows | zl rows ], written
+//                              by pack_kernel in the same swizzled image, one more bulk copy
+//   raw       (kRawL = true)   L block = the fp32 tile itself (16 KiB); z is the caller's
+//                              [columns][4096] tensor read through a 2-D tensor map (hardware
+//                              swizzle, rows past n_cols zero-filled) -- no pack kernel; four
+//                              converter warps write lo = v - trunc_tf32(v) next to the raw tiles
+//                              in shared memory (the tensor core ignores the 13 low mantissa
+//                              bits of an fp32 operand, so the raw tile IS the hi operand)
 //
-// fp32-GRADE ACCURACY FROM TF32 TENSOR CORES.  L = Lh + Ll, z = zh + zl (each part exactly
-// representable in tf32, hi rounded rna), and  L z ~= Lh zh + (Lh zl + Ll zh); the dropped
-// Ll zl term is ~2^-22 relative.  Per 8 k values the issuer sends TWO MMAs:
-//     D[:, 0:2nb]  += Lh x [zh | zl]      (N = 2 nb: main product and first correction side by side)
-//     D[:, nb:2nb] += Ll x  zh            (N = nb:   second correction)
-// so Lh is read from shared memory once instead of twice, and the large main sums never share an
-// accumulator with the small corrections.  The tensor core ADDS INTO TMEM WITH TRUNCATION (measured:
-// error grows with the length of the in-TMEM chain and is biased towards zero), so a chain is
-// cut after `chain` stages (4 => 16 adds): the epilogue warps pull the two accumulator halves
-// out of TMEM, add them in fp32 round-to-nearest into per-thread running sums, and the issuer
-// carries on in the other TMEM buffer meanwhile.
+// fp32-GRADE ACCURACY FROM TF32 TENSOR CORES.  L = Lh + Ll, z = zh + zl, and
+// L z ~= Lh zh + (Lh zl + Ll zh); the dropped Ll zl term is ~2^-22 relative.  Per 8 k values the
+// issuer sends TWO MMAs:  Lh x [zh | zl]  (N = 2 nb: main product and first correction side by
+// side) and  Ll x zh  (N = nb: second correction), so Lh is read from shared memory once and the
+// large main sums never share an accumulator with the small corrections.  The tensor core ADDS
+// INTO TMEM WITH TRUNCATION (measured: error grows with the length of the in-TMEM chain and is
+// biased towards zero), so a chain is cut after `chain` k-stages (4 => 16 adds): the epilogue
+// warps pull the accumulators out of TMEM, add them in fp32 round-to-nearest into per-thread
+// running sums, and the issuer carries on in the other TMEM buffer meanwhile.
 //
-// PERSISTENT, STREAM-K.  The W = (column blocks) x (stages) units are cut into G = min(#SMs, W)
-// equal contiguous ranges, one per CTA, so every SM streams the same number of L bytes and
-// issues the same number of MMAs (+-1 stage) whatever the triangle looks like.  A CTA's range
-// crosses row-tile borders; each maximal piece inside one row tile is a SEGMENT written out as
-// one partial tile P[slot][column][128 rows], slot = cta + tile index (unique).  The combine
-// kernel (noise_epilogue.cu) adds the partials of a row tile in ascending k order in fp32 --
-// deterministic, no atomics on data.
+// PERSISTENT, STREAM-K.  The W = (column blocks) x (schedule units) are cut into G = min(#SMs, W)
+// equal contiguous ranges, one per CTA (row tiles visited longest first), so every SM streams the
+// same number of L bytes whatever the triangle looks like.  A CTA's range crosses row-tile
+// borders; each maximal piece inside one row tile is a SEGMENT written out as one partial tile
+// P[slot][column][128 rows], slot = cta + visit index (unique).  The combine kernel
+// (noise_epilogue.cu) adds the partials of a row tile in ascending k order in fp32 --
+// deterministic, no atomics on data.  (Optionally the last CTA to finish a row tile combines it
+// in-kernel: implemented, tested, off by default -- see DESIGN.md.)
 //
-// CTA = 6 warps: warp 0 = producer (1 lane issues the bulk copies), warp 1 = TMEM alloc + MMA
-// issuer (1 lane), warps 2..5 = epilogue.  Pipelines: smem stage ring (producer <-> issuer),
-// two TMEM accumulator buffers (issuer <-> epilogue), the static stream-K schedule.
+// CTA: warp 0 = producer, warp 1 = TMEM alloc + MMA issuer (both warp-uniform with elect.sync, so
+// descriptors stay in uniform registers), warps 2..5 = epilogue, warps 6..9 = converter (raw
+// variant).  Pipelines: smem stage ring (producer <-> [converter <->] issuer), two TMEM
+// accumulator buffers (issuer <-> epilogue), the static stream-K schedule.  Launched with
+// programmatic stream serialisation: L loads go out before griddepcontrol.wait.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
