@@ -16,6 +16,7 @@
 // channels-per-group is a multiple of 4) and walks the pixels; statistics are per-thread shifted
 // sums merged with Chan's parallel-variance formula in a FIXED order (bit-reproducible).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
     // ---- moments of this CTA's slab (s = x + add is written back so the second pass reads s) -----
     float shift = 0.f, sum = 0.f, sq = 0.f, cnt = 0.f;
     if (tid < n_quads) shift = tile[tid].x + add.x;
+#pragma unroll 4
     for (int i = tid; i < n_quads; i += nt) {
       float4 s = tile[i];
       s.x += add.x; s.y += add.y; s.z += add.z; s.w += add.w;
@@ -321,8 +323,10 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
     __syncthreads();
 
     // ---- normalise + affine + activation out of shared memory; refill consumed slots with the next item ----
+    // y = s * sc + sh with sc = rstd * weight, sh = bias - mean * sc (the form PyTorch's GroupNorm uses too)
     const float mean = s_mean[g_local], rstd = s_rstd[g_local];
     const float4 sc = make_float4(rstd * w.x, rstd * w.y, rstd * w.z, rstd * w.w);
+    const float4 sh = make_float4(bi.x - mean * sc.x, bi.y - mean * sc.y, bi.z - mean * sc.z, bi.w - mean * sc.w);
     float4 *y4 = reinterpret_cast<float4 *>(a.y + ((size_t)b * a.HW + px0) * a.C + c0) + (size_t)prow * rowq + cq;
     const size_t ystep = (size_t)pstep * rowq;
     const int next = item + n_clusters;
@@ -337,10 +341,10 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
         nsrc += nstep;
       }
       float4 o;
-      o.x = (s.x - mean) * sc.x + bi.x;
-      o.y = (s.y - mean) * sc.y + bi.y;
-      o.z = (s.z - mean) * sc.z + bi.z;
-      o.w = (s.w - mean) * sc.w + bi.w;
+      o.x = fmaf(s.x, sc.x, sh.x);
+      o.y = fmaf(s.y, sc.y, sh.y);
+      o.z = fmaf(s.z, sc.z, sh.z);
+      o.w = fmaf(s.w, sc.w, sh.w);
       if (a.silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
       *y4 = o;
     }
@@ -411,8 +415,15 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
   if (!res && !sum_out) {
     // cluster path: P CTAs per (sample, channel block), slab of HW / P pixels in shared memory
     const size_t row_bytes = (size_t)cblk * 4;
+    static int slab_kb = 0;      // BNDM_GN_SLAB_KB: target slab size per CTA (experiments); default 64
+    if (!slab_kb) {
+      const char *e = getenv("BNDM_GN_SLAB_KB");
+      slab_kb = e ? atoi(e) : 64;
+      if (slab_kb < 8 || slab_kb > 192) slab_kb = 64;
+    }
+    const int p_max = slab_kb < 64 ? 16 : 8;
     int P = 1;
-    while (P < 8 && ((size_t)((HW + P - 1) / P) * row_bytes > 64 * 1024)) P *= 2;
+    while (P < p_max && ((size_t)((HW + P - 1) / P) * row_bytes > (size_t)slab_kb * 1024)) P *= 2;
     if ((size_t)((HW + P - 1) / P) * row_bytes > 200 * 1024) P = 16;     // 128^2 images: non-portable cluster size
     const int ppc = (HW + P - 1) / P;
     const size_t smem = (size_t)ppc * row_bytes;
