@@ -6,7 +6,7 @@
 TAG=${1:-r01}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-KERNELS='gemm_tc_kernel|iadb_step_kernel|pack_kernel|combine_kernel|groupnorm_nhwc|add_bias_nhwc|attention_small|upsample2x'
+KERNELS='gemm_tc_kernel|iadb_step_kernel|ddim_step_kernel|to_u8_kernel|pack_kernel|combine_kernel|groupnorm_nhwc|add_bias_nhwc|attention_small|upsample2x'
 keep_small() { if [ -f "$1" ] && [ $(stat -c %s "$1") -gt 20000000 ]; then rm -f "$1"; fi; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt
@@ -19,7 +19,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --
   python bench.py --steps 1 --warmup 1 --nb-steps 1 --no-cpu-baseline --no-extras > $OUT/ncu_bench.log 2>&1
 python tools/summarize_launches.py $OUT/launches.csv > $OUT/launches_summary.txt 2>&1; tail -12 $OUT/launches_summary.txt
 echo "== ncu --set full, get_noise + K2 micro driver (cfg1 B=4, cfg2 B=64, K2 at three shapes)"
-timeout 400 ncu --set full --clock-control none -k regex:"$KERNELS" -c 26 -f -o $OUT/prof_micro \
+timeout 400 ncu --set full --clock-control none -k regex:"$KERNELS" -c 58 -f -o $OUT/prof_micro \
   env NO_GRAPH_TIMING=1 python tools/k_micro.py --k2 --iters 0 --flush write > $OUT/ncu_micro.log 2>&1
 python tools/ncu_summary.py $OUT/prof_micro.ncu-rep > $OUT/ncu_micro_summary.txt 2>&1; keep_small $OUT/prof_micro.ncu-rep
 echo "== ncu --set full, K5 at two UNet shapes"

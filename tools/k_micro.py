@@ -110,6 +110,28 @@ if args.k2:
         print(f"K2 B={B} C={C} Cd={Cd} HW={HW}: us = {[round(t, 1) for t in ts]} median {med:.1f} "
               f"({nbytes / med / 1e3:.0f} GB/s with event overhead)", flush=True)
 
+if args.k2:
+    # K3 (DDIM step, cfg 3: B=64, 3x64x64, eta = 0 and eta = 1 with a noise field) and K4 (uint8 NHWC)
+    from bndm_b200.ddim import DDIMScheduler, ddim_step_raw
+    from bndm_b200.io import to_uint8_nhwc
+    sch = DDIMScheduler()
+    sch.set_timesteps(100)
+    B = 64
+    x = torch.randn(B, 3, 64, 64, device=dev)
+    eps = torch.randn_like(x)
+    nz = torch.randn_like(x)
+    t_vec = torch.zeros(B, device=dev)
+    for eta, noise in ((0.0, None), (1.0, nz)):
+        table = sch.coefficient_table(eta).to(dev)
+        state = torch.zeros(2, dtype=torch.int32, device=dev)
+        ts = timed(lambda: ddim_step_raw(x, x, eps, noise, table, state, t_vec), 6)
+        nbytes = 4 * x.numel() * (3 + (noise is not None))
+        med = statistics.median(ts[2:] or ts)
+        print(f"K3 DDIM step B={B} eta={eta}: us = {[round(t, 1) for t in ts]} median {med:.1f} "
+              f"({nbytes / med / 1e3:.0f} GB/s with event overhead)", flush=True)
+    ts = timed(lambda: to_uint8_nhwc(x), 6)
+    print(f"K4 to_uint8_nhwc B={B}: us = {[round(t, 1) for t in ts]}", flush=True)
+
 # ---- K1b duration vs amount of work (544 / 2112 / 4096 stages per column block): overhead + slope
 if os.environ.get("K1_SCALING"):
     from bndm_b200 import _lib
