@@ -103,6 +103,11 @@ class DDIMScheduler:
 
 
 def ddim_step_raw(out, x, eps, noise, coef_rows, state, t_next_out, clip=True):
+    # K3 indexes flat NCHW memory: a channels-last model output (the fused UNet's native layout) or any
+    # other strided tensor is made contiguous first (a no-op for ordinary outputs)
+    eps = _lib.require_cuda_f32(eps, "model output")
+    if noise is not None:
+        noise = _lib.require_cuda_f32(noise, "variance noise")
     with torch.cuda.device(x.device):
         rc = _lib.load().bndm_ddim_step_f32(_lib.ptr(out), _lib.ptr(x), _lib.ptr(eps), _lib.ptr(noise),
                                             _lib.ptr(coef_rows), _lib.ptr(state), _lib.ptr(t_next_out), x.shape[0],

@@ -331,3 +331,25 @@ def test_upsample2x_nhwc_is_exact(B, C, H, W):
     got = upsample2x_nhwc(x)
     assert got.is_contiguous(memory_format=torch.channels_last)
     assert torch.equal(got, torch.nn.functional.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_sample_ddim_with_channels_last_model_output(use_graph):
+    """A model that returns its prediction in channels-last memory (like FusedUNet2D) must give the
+    same DDIM trajectory as the same model returning NCHW memory."""
+    from types import SimpleNamespace
+
+    class CL:
+        def __init__(self, inner, channels_last):
+            self.inner, self.cl = inner, channels_last
+
+        def __call__(self, x, t, return_dict=True):
+            y = self.inner(x, t).sample
+            if self.cl:
+                y = y.contiguous(memory_format=torch.channels_last)
+                assert not y.is_contiguous()
+            return SimpleNamespace(sample=y)
+    x = torch.randn(3, 3, 16, 16, device=DEV)
+    a = sample_ddim(CL(ToyEps(3), False), x, 10, use_graph=use_graph)
+    b = sample_ddim(CL(ToyEps(3), True), x, 10, use_graph=use_graph)
+    assert torch.equal(a, b)
