@@ -417,6 +417,37 @@ def run_ours(args):
 
     if rank == 0 and not args.no_extras:
         line["get_noise"] = get_noise_micro(torch, bb, dev, L, handle, pk)
+        # K2 without the per-launch event overhead (a CUDA-event pair around a ~4 us kernel costs as much as
+        # the kernel): one CUDA graph of 50 scheduled steps on the sampler's own buffers, x / d L2-resident
+        # as in the sampling loop
+        try:
+            st = sampler.stepper
+            st.reset()
+            d_probe = torch.randn(B, OUT_CH, RES, RES, device=dev)
+            if args.unet == "fused" and args.unet_dtype == "fp32":
+                d_probe = d_probe.contiguous(memory_format=torch.channels_last)
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                st.step_(sampler.x, d_probe)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            st.reset()
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(50):
+                    st.step_(sampler.x, d_probe)
+            ts = []
+            for _ in range(5):
+                st.reset()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); g.replay(); e1.record(); e1.synchronize()
+                ts.append(e0.elapsed_time(e1) / 50)
+            k2_graph_ms = statistics.median(ts)
+            line["roofline_step"]["ms_per_launch_in_graph"] = k2_graph_ms
+            line["roofline_step"]["achieved_in_graph"] = k2_bytes / (k2_graph_ms * 1e-3) / 1e9
+            line["roofline_step"]["frac_in_graph"] = k2_bytes / (k2_graph_ms * 1e-3) / 1e9 / pk["hbm_gbs"]
+        except Exception as e:          # measurement extra only
+            line["roofline_step"]["in_graph_error"] = repr(e)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, det = cpu_reference_sample(args.cpu_batch, args.cpu_steps, T, threads, L_np)

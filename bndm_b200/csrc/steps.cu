@@ -124,6 +124,48 @@ __global__ void __launch_bounds__(256, kStepBlocksPerSM) iadb_step_kernel(IadbAr
     for (int b = threadIdx.x; b < a.B; b += blockDim.x) a.t_next_out[b] = __ldg(rows + b).z;
 }
 
+// Scheduled step with the UNet output in channels-last memory (d[b][hw][Cd]) and C <= 4: one thread per
+// PIXEL -- consecutive lanes read consecutive 4*Cd-byte pixel records of d and consecutive floats of
+// every x plane, so every access is coalesced (the generic kernel's per-channel mapping strides through
+// d).  Same arithmetic, same ticket scheme.
+constexpr int kNhwcMaxC = 4;
+__global__ void __launch_bounds__(256, kStepBlocksPerSM) iadb_step_dnhwc_kernel(IadbArgs a) {
+  const bool two = a.Cd == 2 * a.C;
+  const unsigned total = (unsigned)a.B * a.HW;
+  const unsigned stride = gridDim.x * blockDim.x;
+  unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  float xv[kNhwcMaxC], u[kNhwcMaxC], v[kNhwcMaxC];
+  int b = 0;
+  unsigned p = 0;
+  auto fetch = [&]() {
+    b = (int)(idx / (unsigned)a.HW);
+    p = idx - (unsigned)b * a.HW;
+    const float *dp = a.d + (int64_t)idx * a.Cd;
+#pragma unroll
+    for (int c = 0; c < kNhwcMaxC; ++c)
+      if (c < a.C) {
+        xv[c] = a.x[((int64_t)b * a.C + c) * a.HW + p];
+        u[c] = __ldg(dp + c);
+        v[c] = two ? __ldg(dp + a.C + c) : 0.f;
+      }
+  };
+  if (idx < total) fetch();
+  bool publishes = false;
+  const int step = step_from_ticket(a.state, publishes);
+  const float4 *rows = reinterpret_cast<const float4 *>(a.table) + (int64_t)step * a.B;
+  while (idx < total) {
+    const float4 row = __ldg(rows + b);
+#pragma unroll
+    for (int c = 0; c < kNhwcMaxC; ++c)
+      if (c < a.C)
+        a.x_out[((int64_t)b * a.C + c) * a.HW + p] = two ? upd2(xv[c], u[c], row.x, v[c], row.y) : upd1(xv[c], u[c], row.x);
+    idx += stride;                        // at most ~1.2 elements per thread: no look-ahead needed
+    if (idx < total) fetch();
+  }
+  if (publishes && a.t_next_out)
+    for (int bb = threadIdx.x; bb < a.B; bb += blockDim.x) a.t_next_out[bb] = __ldg(rows + bb).z;
+}
+
 static int grid_for(int64_t work_items, int threads) {
   // at most one full wave (148 SMs x kStepBlocksPerSM resident blocks); grid-stride covers the rest
   int64_t blocks = (work_items + threads - 1) / threads;
@@ -138,6 +180,10 @@ cudaError_t launch_iadb_step(const IadbArgs &a, bool sched, cudaStream_t s) {
                                         reinterpret_cast<uintptr_t>(a.x_out)) % 16 == 0);
   const int64_t total = (int64_t)a.B * a.C * (a.HW / (vec ? 4 : 1));
   if (total >= (int64_t)1 << 31) return cudaErrorInvalidValue;      // 32-bit index math in the kernel
+  if (sched && a.d_nhwc && a.C <= kNhwcMaxC) {
+    iadb_step_dnhwc_kernel<<<grid_for((int64_t)a.B * a.HW, 256), 256, 0, s>>>(a);
+    return cudaGetLastError();
+  }
   const int grid = grid_for(total, 256);
   if (sched) {
     if (vec) iadb_step_kernel<true, true><<<grid, 256, 0, s>>>(a);

@@ -109,6 +109,11 @@ if args.k2:
         med = statistics.median(ts[2:] or ts)
         print(f"K2 B={B} C={C} Cd={Cd} HW={HW}: us = {[round(t, 1) for t in ts]} median {med:.1f} "
               f"({nbytes / med / 1e3:.0f} GB/s with event overhead)", flush=True)
+        d_cl = d.contiguous(memory_format=torch.channels_last)
+        ts = timed(lambda: st.step_(x, d_cl), 6)
+        med = statistics.median(ts[2:] or ts)
+        print(f"K2 (d channels-last) B={B} C={C} Cd={Cd} HW={HW}: us = {[round(t, 1) for t in ts]} median {med:.1f} "
+              f"({nbytes / med / 1e3:.0f} GB/s with event overhead)", flush=True)
 
 if args.k2:
     # K3 (DDIM step, cfg 3: B=64, 3x64x64, eta = 0 and eta = 1 with a noise field) and K4 (uint8 NHWC)
