@@ -32,6 +32,7 @@ SIGNATURES = {
     "bndm_profile_enable": (C.c_int, [_P, C.c_int]),
     "bndm_profile_last_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "bndm_get_noise_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_uint, _P]),
+    "bndm_get_noise_train_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_uint, _P]),
     "bndm_white128_reinterpret_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "bndm_iadb_step_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_iadb_step_sched_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

@@ -261,9 +261,11 @@ int bndm_free_L(bndm_L *h) {
   return BNDM_OK;
 }
 
-int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out, float *out_bn, float *out_wn, int B,
-                       int C, int res, unsigned flags, void *stream) {
-  if (!h || !z || !out) { set_error("bndm_get_noise_f32: null argument"); return BNDM_ERR_ARG; }
+}  // extern "C"
+
+static int get_noise_impl(bndm_L *h, const float *z, const float *gamma, float *out, float *out_bn, float *out_wn, int B,
+                          int C, int res, unsigned flags, void *stream, const TrainOut &train) {
+  if (!h || !z || (!out && !train.x_alpha)) { set_error("bndm_get_noise_f32: null argument"); return BNDM_ERR_ARG; }
   if (B < 1 || C < 1) { set_error("bndm_get_noise_f32: bad shape B=%d C=%d", B, C); return BNDM_ERR_ARG; }
   int mode;
   if (res == 64) mode = kRes64;
@@ -339,6 +341,7 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
     ep.C = C;
     ep.res_mode = mode;
     ep.sched = sched;
+    ep.train = train;
     CK(launch_epilogue(ep, s));
   } else {
     // K1b (tcgen05, persistent stream-K) -> K1c (ordered combine + lerp + layout)
@@ -362,7 +365,7 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
     g.trace = h->trace;
     // small column blocks: the combine is fused into the contraction (the last CTA to finish a
     // row tile sums its partial tiles); large ones keep the wide combine kernel
-    const bool fused = tc_fused_combine(nb) && sk.n_colblk * sk.n_tiles <= kMaxTileCounters;
+    const bool fused = !train.x_alpha && tc_fused_combine(nb) && sk.n_colblk * sk.n_tiles <= kMaxTileCounters;
     g.tile_counters = h->tile_counters;
     g.z_cols = z_cols;
     g.gamma = gamma;
@@ -399,6 +402,7 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
     cb.C = C;
     cb.res_mode = mode;
     cb.sk = sk;
+    cb.train = train;
     CK(launch_combine(cb, s));
   }
   if (prof) {
@@ -406,6 +410,24 @@ int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out
     h->ev_valid = 1;
   }
   return BNDM_OK;
+}
+
+extern "C" {
+
+int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out, float *out_bn, float *out_wn, int B,
+                       int C, int res, unsigned flags, void *stream) {
+  if (!out) { set_error("bndm_get_noise_f32: null argument"); return BNDM_ERR_ARG; }
+  return get_noise_impl(h, z, gamma, out, out_bn, out_wn, B, C, res, flags, stream,
+                        TrainOut{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr});
+}
+
+int bndm_get_noise_train_f32(bndm_L *h, const float *z, const float *gamma, const float *x1, const float *alpha,
+                             const float *alpha_prev, float *x_alpha, float *tar1, float *tar2, float *x0, int B, int C, int res,
+                             unsigned flags, void *stream) {
+  if (!x1 || !alpha || !x_alpha || !tar1) { set_error("bndm_get_noise_train_f32: null argument"); return BNDM_ERR_ARG; }
+  if (tar2 && (!alpha_prev || !gamma)) { set_error("bndm_get_noise_train_f32: tar2 needs alpha_prev and gamma"); return BNDM_ERR_ARG; }
+  return get_noise_impl(h, z, gamma, x0, nullptr, nullptr, B, C, res, flags, stream,
+                        TrainOut{x1, alpha, alpha_prev, x_alpha, tar1, tar2});
 }
 
 int bndm_white128_reinterpret_f32(const float *x, float *out, int B, int C, void *stream) {

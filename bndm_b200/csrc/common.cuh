@@ -92,6 +92,16 @@ struct GemmArgs {
 };
 cudaError_t launch_gemm_simt(const GemmArgs &a, cudaStream_t s);
 
+// Training-side fusion (iadb_bn.py:881-954): when x_alpha != null the epilogue also emits
+//   x_alpha = alpha[b] * x0 + (1 - alpha[b]) * x1       (:915, x0 = the lerped noise, x1 = data)
+//   tar1    = x1 - x0                                   (:949 / :976)
+//   tar2    = alpha_prev[b] * (noise_bn - noise_wn)     (:950; null for 'GBN')
+// in the same pass, with the reference's association (explicit _rn ops).
+struct TrainOut {
+  const float *x1, *alpha, *alpha_prev;
+  float *x_alpha, *tar1, *tar2;
+};
+
 struct EpilogueArgs {
   const float *partials;
   const float *z_cols;   // packed raw columns [n_cols_pad][4096] (white values)
@@ -101,6 +111,7 @@ struct EpilogueArgs {
   int B, C;
   int res_mode;
   Schedule sched;
+  TrainOut train;
 };
 cudaError_t launch_epilogue(const EpilogueArgs &a, cudaStream_t s);
 
@@ -202,6 +213,7 @@ struct CombineArgs {
   int B, C;
   int res_mode;
   StreamK sk;
+  TrainOut train;
 };
 cudaError_t launch_combine(const CombineArgs &a, cudaStream_t s);
 

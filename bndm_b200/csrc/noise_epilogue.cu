@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) combine_kernel(CombineArgs a) {
   const float4 *P = reinterpret_cast<const float4 *>(a.partials + (int64_t)sk.slot(c_first, cb, tile) * slot_stride +
                                                      (int64_t)jc * kBlk + rq * 4);
   const int64_t stride4 = slot_stride / 4;
-  const OutMap m{a.z_cols, a.gamma, a.out, a.out_bn, a.out_wn, a.B, a.C, a.res_mode};
+  const OutMap m{a.z_cols, a.gamma, a.out, a.out_bn, a.out_wn, a.B, a.C, a.res_mode, a.train};
   pdl_wait();                   // partial tiles of the contraction are complete and visible
   if (!live) return;
   // one round trip for the common case: the white / gamma loads and up to 8 partial tiles are
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) epilogue_kernel(EpilogueArgs a) {
   const float *P = a.partials + (int64_t)base * stride + (int64_t)j * kBlk + rq * 4;
   float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int s = 0; s < ns; ++s) bn = add4(bn, *reinterpret_cast<const float4 *>(P + (int64_t)s * stride));
-  const OutMap m{a.z_cols, a.gamma, a.out, a.out_bn, a.out_wn, a.B, a.C, a.res_mode};
+  const OutMap m{a.z_cols, a.gamma, a.out, a.out_bn, a.out_wn, a.B, a.C, a.res_mode, a.train};
   emit4(m, j, i * kBlk + rq * 4, bn);
 }
 

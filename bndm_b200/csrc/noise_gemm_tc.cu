@@ -678,7 +678,7 @@ static cudaError_t launch_nb(const TcGemmArgs &g, cudaStream_t s) {
   a.chain = tc_chain() / kSub > 0 ? tc_chain() / kSub : 1;       // schedule units per TMEM chain
   a.trace = g.trace;
   a.tile_counters = g.tile_counters;
-  a.om = OutMap{g.z_cols, g.gamma, g.out, g.out_bn, g.out_wn, g.B, g.C, g.res_mode};
+  a.om = OutMap{g.z_cols, g.gamma, g.out, g.out_bn, g.out_wn, g.B, g.C, g.res_mode, TrainOut{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
   a.n_cols = g.n_cols;
   // L is streamed once per call when there is one column block; with several, the CTAs of the
   // other column blocks read the same stage blocks at about the same time -> keep them in L2

@@ -13,6 +13,7 @@ struct OutMap {
   const float *gamma;
   float *out, *out_bn, *out_wn;
   int B, C, res_mode;
+  TrainOut train = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // 4 consecutive pixels p..p+3 (same image row: p % 4 == 0) of GEMM column j, in two halves so the
@@ -21,6 +22,8 @@ struct OutPos4 {
   int64_t dst;     // flat output index of the first pixel, < 0: cropped away
   float4 wn;
   float g;
+  float4 x1;       // training mode: the data pixels at dst
+  float al, alp;   // training mode: alpha[b], alpha_prev[b]
 };
 __device__ __forceinline__ OutPos4 locate4(const OutMap &m, int j, int p) {
   const int h = p >> 6, w = p & 63;
@@ -53,6 +56,13 @@ __device__ __forceinline__ OutPos4 locate4(const OutMap &m, int j, int p) {
     o.wn = make_float4(t[0], t[1], t[2], t[3]);
   }
   o.g = m.gamma ? __ldg(m.gamma + b) : 0.0f;
+  o.x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  o.al = o.alp = 0.0f;
+  if (m.train.x_alpha && o.dst >= 0) {
+    o.x1 = __ldg(reinterpret_cast<const float4 *>(m.train.x1 + o.dst));
+    o.al = __ldg(m.train.alpha + b);
+    o.alp = m.train.alpha_prev ? __ldg(m.train.alpha_prev + b) : 0.0f;
+  }
   return o;
 }
 __device__ __forceinline__ void store4(const OutMap &m, const OutPos4 &q, float4 bn) {
@@ -66,9 +76,26 @@ __device__ __forceinline__ void store4(const OutMap &m, const OutPos4 &q, float4
     o.z = __fadd_rn(__fmul_rn(bn.z, gi), __fmul_rn(q.wn.z, g));
     o.w = __fadd_rn(__fmul_rn(bn.w, gi), __fmul_rn(q.wn.w, g));
   }
-  *reinterpret_cast<float4 *>(m.out + q.dst) = o;
+  if (m.out) *reinterpret_cast<float4 *>(m.out + q.dst) = o;
   if (m.out_bn) *reinterpret_cast<float4 *>(m.out_bn + q.dst) = bn;
   if (m.out_wn) *reinterpret_cast<float4 *>(m.out_wn + q.dst) = q.wn;
+  if (m.train.x_alpha) {
+    const float a = q.al, ai = __fsub_rn(1.0f, q.al);
+    float4 xa, t1;
+    xa.x = __fadd_rn(__fmul_rn(a, o.x), __fmul_rn(ai, q.x1.x));
+    xa.y = __fadd_rn(__fmul_rn(a, o.y), __fmul_rn(ai, q.x1.y));
+    xa.z = __fadd_rn(__fmul_rn(a, o.z), __fmul_rn(ai, q.x1.z));
+    xa.w = __fadd_rn(__fmul_rn(a, o.w), __fmul_rn(ai, q.x1.w));
+    t1.x = __fsub_rn(q.x1.x, o.x); t1.y = __fsub_rn(q.x1.y, o.y); t1.z = __fsub_rn(q.x1.z, o.z); t1.w = __fsub_rn(q.x1.w, o.w);
+    *reinterpret_cast<float4 *>(m.train.x_alpha + q.dst) = xa;
+    *reinterpret_cast<float4 *>(m.train.tar1 + q.dst) = t1;
+    if (m.train.tar2) {
+      float4 t2;
+      t2.x = __fmul_rn(q.alp, __fsub_rn(bn.x, q.wn.x)); t2.y = __fmul_rn(q.alp, __fsub_rn(bn.y, q.wn.y));
+      t2.z = __fmul_rn(q.alp, __fsub_rn(bn.z, q.wn.z)); t2.w = __fmul_rn(q.alp, __fsub_rn(bn.w, q.wn.w));
+      *reinterpret_cast<float4 *>(m.train.tar2 + q.dst) = t2;
+    }
+  }
 }
 __device__ __forceinline__ void emit4(const OutMap &m, int j, int p, float4 bn) { store4(m, locate4(m, j, p), bn); }
 

@@ -167,3 +167,48 @@ def get_noise_v2(device, x, cov_mat_L, alpha_t, time_step=None, noise_type="gaus
 
 
 get_noise = get_noise_v2   # the name BASELINE.json's north_star uses
+
+
+def get_noise_train(device, x1, cov_mat_L, gamma_t, alpha, alpha_prev=None, noise_type="gaussianBN", *, draw=None,
+                    want_x0=False, gemm="tc"):
+    """The noise + blend front end of one IADB training step (iadb_bn.py:881-954) in one call:
+
+        x0, bn, wn = get_noise_v2(device, x1, L, gamma_t, t, noise_type, 'train', inplace=False)
+        x_alpha = alpha*x0 + (1-alpha)*x1;  tar1 = x1 - x0;  tar2 = alpha_prev*(bn - wn)
+
+    Returns ``(x_alpha, tar1, tar2[, x0])`` (``tar2`` is None for 'GBN' or when ``alpha_prev`` is None).  The
+    white field is drawn exactly where get_noise_v2 draws it (``draw`` overrides it, for tests).  The
+    contraction is the same kernel; only its epilogue differs (5 element-wise passes and 3 temporaries
+    less than the torch sequence)."""
+    if noise_type not in BLUE_TYPES:
+        raise NotImplementedError
+    x1 = _lib.require_cuda_f32(x1, "x1")
+    bs, C, res = x1.shape[0], x1.shape[1], x1.shape[-1]
+    if res not in (32, 64, 128):
+        raise NotImplementedError
+    L = prepare_L(cov_mat_L, max_columns=bs * C * (4 if res == 128 else 1))
+    if draw is not None:
+        z = _lib.require_cuda_f32(draw, "draw")
+    elif res == 64:
+        z = torch.randn_like(x1)
+    elif res == 32:
+        z = torch.randn(bs, C, 64, 64, dtype=x1.dtype, device=x1.device)
+    else:
+        z = _lib.require_cuda_f32(torch.randn(bs * 4, C, 64, 64).float().to(device), "white draw")
+    gamma = None
+    if noise_type in ("gaussianBN", "gaussianRN"):
+        gamma = _lib.require_cuda_f32(gamma_t.reshape(-1), "gamma_t")
+    alpha = _lib.require_cuda_f32(alpha.reshape(-1), "alpha")
+    two = gamma is not None and alpha_prev is not None
+    if two:
+        alpha_prev = _lib.require_cuda_f32(alpha_prev.reshape(-1), "alpha_prev")
+    x_alpha, tar1 = torch.empty_like(x1), torch.empty_like(x1)
+    tar2 = torch.empty_like(x1) if two else None
+    x0 = torch.empty_like(x1) if want_x0 else None
+    with torch.cuda.device(x1.device):
+        rc = _lib.load().bndm_get_noise_train_f32(L._h, _lib.ptr(z), _lib.ptr(gamma), _lib.ptr(x1), _lib.ptr(alpha),
+                                                  _lib.ptr(alpha_prev if two else None), _lib.ptr(x_alpha), _lib.ptr(tar1),
+                                                  _lib.ptr(tar2), _lib.ptr(x0), bs, C, res, _lib.SRC_DRAW | _GEMM_FLAGS[gemm],
+                                                  _lib.current_stream(x1.device))
+    _lib.check(rc, "bndm_get_noise_train_f32")
+    return (x_alpha, tar1, tar2, x0) if want_x0 else (x_alpha, tar1, tar2)

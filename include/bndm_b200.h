@@ -92,6 +92,20 @@ int bndm_profile_last_ms(bndm_L *h, float *pack_ms, float *gemm_ms, float *epilo
 int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out, float *out_bn,
                        float *out_wn, int B, int C, int res, unsigned flags, void *stream);
 
+/* Training-side fusion (iadb_bn.py:881-954, latent_iadb_bn_diffusers.py:606-633): the
+ * same contraction, with the epilogue emitting what the training step builds from get_noise_v2's
+ * three results instead of (or next to) them:
+ *     x0      = bn*(1-gamma[b]) + wn*gamma[b]             (gamma == NULL: x0 = bn, 'GBN')
+ *     x_alpha = alpha[b]*x0 + (1-alpha[b])*x1             iadb_bn.py:915  (x1 = data batch, dev (B,C,res,res))
+ *     tar1    = x1 - x0                                   iadb_bn.py:949,976
+ *     tar2    = alpha_prev[b]*(bn - wn)                   iadb_bn.py:950  (NULL: not written)
+ * alpha, alpha_prev: dev [B].  x0 may be NULL.  z / flags as bndm_get_noise_f32 (the training loop
+ * draws: inplace=False => BNDM_SRC_DRAW).  fp32 with the reference's association => bit-identical
+ * to the torch expressions applied to this library's (x0, bn, wn).                            */
+int bndm_get_noise_train_f32(bndm_L *h, const float *z, const float *gamma, const float *x1, const float *alpha,
+                             const float *alpha_prev, float *x_alpha, float *tar1, float *tar2, float *x0,
+                             int B, int C, int res, unsigned flags, void *stream);
+
 /* 'gaussian' pass-through at 128^2 with train_or_test=='test' (get_noise_recent.py:50-56):
  * out = noise_padding(reinterpret(quadrants(x))).  x, out: (B,C,128,128), no aliasing.     */
 int bndm_white128_reinterpret_f32(const float *x, float *out, int B, int C, void *stream);

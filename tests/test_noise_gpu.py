@@ -272,3 +272,28 @@ def test_unit_variance_blue_L_accuracy(bs):
         bn = bb.get_noise_v2(DEV, x, L, None, None, "GBN", "train", True, gemm=gemm)[1]
         err = (bn.double() - ref).abs().max().item()
         assert err < (4e-6 if gemm == "tc" else ATOL), (gemm, err)
+
+
+# ------------------------------------------------------------------ training-side fusion
+@pytest.mark.parametrize("gemm", GEMMS)
+@pytest.mark.parametrize("res,bs,C,noise_type", [(64, 6, 3, "gaussianBN"), (64, 64, 3, "gaussianBN"), (32, 4, 4, "gaussianBN"),
+                                                 (128, 2, 3, "gaussianBN"), (64, 5, 3, "GBN")])
+def test_get_noise_train_equals_the_torch_sequence(res, bs, C, noise_type, gemm, L_dev):
+    """x_alpha / tar1 / tar2 from the fused epilogue == the reference's expressions (iadb_bn.py:915,949-950)
+    applied to this library's own (x0, bn, wn) for the same draw, bit for bit."""
+    g = torch.Generator(device="cpu").manual_seed(res + bs)
+    x1 = (torch.rand(bs, C, res, res, generator=g) * 2 - 1).to(DEV)
+    draw = torch.randn(bs * (4 if res == 128 else 1), C, 64, 64, generator=g).to(DEV)
+    gamma = torch.rand(bs, generator=g).to(DEV)
+    alpha = torch.rand(bs, generator=g).to(DEV)
+    alpha_prev = torch.rand(bs, generator=g).to(DEV)
+    x0, bn, wn = _call_with_draw(L_dev, draw, gamma, x1.shape, noise_type, gemm)
+    xa, t1, t2, x0f = bb.get_noise_train(DEV, x1, L_dev, gamma, alpha, alpha_prev, noise_type, draw=draw, want_x0=True, gemm=gemm)
+    a4 = alpha.view(-1, 1, 1, 1)
+    assert torch.equal(x0f, x0)
+    assert torch.equal(xa, a4 * x0 + (1 - a4) * x1)
+    assert torch.equal(t1, x1 - x0)
+    if noise_type == "GBN":
+        assert t2 is None
+    else:
+        assert torch.equal(t2, alpha_prev.view(-1, 1, 1, 1) * (bn - wn))
