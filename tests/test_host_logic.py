@@ -202,3 +202,19 @@ def test_streamk_schedule_is_consistent():
                     assert rc == 0, (n_tiles, dense, n_colblk, sms, lib.bndm_last_error())
                     rc = lib.bndm_debug_streamk_check_sub(n_tiles, dense, n_colblk, sms, 2)    # 64-k pipeline stages
                     assert rc == 0, (n_tiles, dense, n_colblk, sms, "sub=2", lib.bndm_last_error())
+
+
+def test_fused_unet_and_training_front_end_refuse_cpu():
+    """No CPU fallback anywhere in the product: the fused evaluator and the training-side entry raise."""
+    import bndm_b200 as bb
+    from bndm_b200.fused_unet import fuse_unet, groupnorm_silu_nhwc
+    from bndm_b200.unet import get_latent_model
+    model = get_latent_model(256, 8)
+    with pytest.raises(bb.BndmError):
+        fuse_unet(model)                                   # float32 but on the CPU
+    with pytest.raises(TypeError):
+        fuse_unet(torch.nn.Linear(2, 2))
+    with pytest.raises(bb.BndmError):
+        groupnorm_silu_nhwc(torch.randn(1, 128, 4, 4), torch.nn.GroupNorm(32, 128))
+    with pytest.raises(bb.BndmError):
+        bb.get_noise_train(torch.device("cpu"), torch.randn(2, 3, 64, 64), torch.eye(4096), torch.ones(2), torch.ones(2))
