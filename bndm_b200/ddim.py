@@ -15,6 +15,8 @@ loop.  ``noise_fn`` lets eta > 0 steps take their variance noise from ``get_nois
 """
 from __future__ import annotations
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -116,20 +118,21 @@ def ddim_step_raw(out, x, eps, noise, coef_rows, state, t_next_out, clip=True):
     return out
 
 
+_graph_cache: "dict[tuple, dict]" = {}      # captured [UNet, K3] steps, see sample_ddim
+
+
 @torch.no_grad()
 def sample_ddim(model, x, num_inference_steps, eta=0.0, noise_fn=None, scheduler=None, use_graph=False,
                 snapshots=False):
     """for t in scheduler.timesteps: eps = model(x, t).sample; x = scheduler.step(eps, t, x).prev_sample
     (ddim_diffusers.py:674-683).  ``noise_fn(i, t, x) -> variance noise`` when eta > 0.
-    With ``use_graph`` the [UNet, K3] pair is captured once (only when noise_fn is None)."""
+    With ``use_graph`` (eta == 0) the [UNet, K3] pair is captured once per (model, shape, schedule) and kept:
+    repeated calls replay it instead of re-capturing."""
     scheduler = scheduler or DDIMScheduler()
     scheduler.set_timesteps(num_inference_steps)
-    x = _lib.require_cuda_f32(x, "x").clone()
-    B = x.shape[0]
-    table = scheduler.coefficient_table(eta).to(x.device)
-    state = torch.zeros(2, dtype=torch.int32, device=x.device)
+    x_in = _lib.require_cuda_f32(x, "x")
+    B = x_in.shape[0]
     ts = [int(t) for t in scheduler.timesteps]
-    t_vec = torch.full((B,), float(ts[0]), dtype=torch.float32, device=x.device)
 
     def call(xx, tt):
         out = model(xx, tt)
@@ -137,19 +140,42 @@ def sample_ddim(model, x, num_inference_steps, eta=0.0, noise_fn=None, scheduler
 
     seqs = []
     graph = None
-    if use_graph and (eta == 0 or noise_fn is None) and eta == 0:
-        side = torch.cuda.Stream(device=x.device)
-        side.wait_stream(torch.cuda.current_stream(x.device))
-        keep = x.clone()
-        with torch.cuda.stream(side):
-            for _ in range(2):
+    graphable = bool(use_graph) and eta == 0
+    key = (id(model), tuple(x_in.shape), str(x_in.device), num_inference_steps, scheduler.num_train_timesteps,
+           bool(scheduler.clip_sample))
+    entry = _graph_cache.get(key) if graphable else None
+    if entry is not None and entry["model_ref"]() is not model:       # id() reuse after garbage collection
+        entry = None
+    if entry is not None:
+        x, table, state, t_vec, graph = entry["x"], entry["table"], entry["state"], entry["t_vec"], entry["graph"]
+        x.copy_(x_in)
+        state.zero_()
+        t_vec.fill_(float(ts[0]))
+    else:
+        x = x_in.clone()
+        table = scheduler.coefficient_table(eta).to(x.device)
+        state = torch.zeros(2, dtype=torch.int32, device=x.device)
+        t_vec = torch.full((B,), float(ts[0]), dtype=torch.float32, device=x.device)
+        if graphable:
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            keep = x.clone()
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    ddim_step_raw(x, x, call(x, t_vec), None, table, state, t_vec, scheduler.clip_sample)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            x.copy_(keep); state.zero_(); t_vec.fill_(float(ts[0]))
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
                 ddim_step_raw(x, x, call(x, t_vec), None, table, state, t_vec, scheduler.clip_sample)
-        torch.cuda.current_stream(x.device).wait_stream(side)
-        x.copy_(keep); state.zero_(); t_vec.fill_(float(ts[0]))
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            ddim_step_raw(x, x, call(x, t_vec), None, table, state, t_vec, scheduler.clip_sample)
-        x.copy_(keep); state.zero_(); t_vec.fill_(float(ts[0]))
+            x.copy_(keep); state.zero_(); t_vec.fill_(float(ts[0]))
+            try:
+                ref = weakref.ref(model)
+            except TypeError:
+                ref = (lambda m: (lambda: m))(model)
+            if len(_graph_cache) >= 4:
+                _graph_cache.pop(next(iter(_graph_cache)))
+            _graph_cache[key] = {"x": x, "table": table, "state": state, "t_vec": t_vec, "graph": graph, "model_ref": ref}
 
     for i, t in enumerate(ts):
         if graph is not None:
@@ -163,4 +189,6 @@ def sample_ddim(model, x, num_inference_steps, eta=0.0, noise_fn=None, scheduler
             ddim_step_raw(x, x, eps, vn, table, state, t_vec, scheduler.clip_sample)
         if snapshots and t % 100 == 0:                 # ddim_diffusers.py:682-683
             seqs.append(x[0:1].clone())
+    if graph is not None:
+        x = x.clone()                                  # the static buffer belongs to the cached graph
     return (x, seqs) if snapshots else x

@@ -342,7 +342,18 @@ def sample_latent_iadb(model, noise, num_steps, noise_type="gaussianBN", out_cha
             raise NotImplementedError
     elif noise_type != "gaussian":
         raise NotImplementedError
-    table, first_t = latent_table(num_steps, batch=x.shape[0])
-    sampler = IadbSampler(model, x.shape, num_steps, out_channel=out_channels, noise_type=noise_type, device=x.device,
-                          graph="step" if use_graph else None, table=table, first_t=first_t)
+    # graph mode: the captured [UNet -> K2] step is kept per (model, shape, schedule) like sample_iadb's,
+    # so repeated calls (a sampling job runs hundreds of batches) replay instead of re-capturing
+    key = ("latent", id(model), tuple(x.shape), str(x.device), num_steps, noise_type, out_channels)
+    sampler = _sampler_cache.get(key) if use_graph else None
+    if sampler is not None and sampler._model_ref() is not model:      # id() reuse after garbage collection
+        sampler = None
+    if sampler is None:
+        table, first_t = latent_table(num_steps, batch=x.shape[0])
+        sampler = IadbSampler(model, x.shape, num_steps, out_channel=out_channels, noise_type=noise_type, device=x.device,
+                              graph="step" if use_graph else None, table=table, first_t=first_t)
+        if use_graph:
+            if len(_sampler_cache) >= 4:
+                _sampler_cache.pop(next(iter(_sampler_cache)))
+            _sampler_cache[key] = sampler
     return sampler(x)

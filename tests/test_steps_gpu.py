@@ -353,3 +353,27 @@ def test_sample_ddim_with_channels_last_model_output(use_graph):
     a = sample_ddim(CL(ToyEps(3), False), x, 10, use_graph=use_graph)
     b = sample_ddim(CL(ToyEps(3), True), x, 10, use_graph=use_graph)
     assert torch.equal(a, b)
+
+
+def test_graph_samplers_are_cached_and_stay_correct_across_calls():
+    """sample_ddim / sample_latent_iadb keep their captured step per (model, shape, schedule): the second call
+    replays the cached graph on new inputs and must equal the eager loop for those inputs."""
+    from bndm_b200 import ddim as bd
+    from bndm_b200.unet import get_latent_model
+    eps_model = ToyEps(3)
+    xs = [torch.randn(3, 3, 16, 16, device=DEV) for _ in range(3)]
+    graphs = set()
+    for x in xs:
+        got = sample_ddim(eps_model, x, 10, use_graph=True)
+        want = sample_ddim(eps_model, x, 10, use_graph=False)
+        assert torch.equal(got, want)
+        graphs.add(id([e for k, e in bd._graph_cache.items() if k[0] == id(eps_model)][0]["graph"]))
+    assert len(graphs) == 1 and len(bd._graph_cache) <= 4, "one captured graph serves all three calls"
+    torch.manual_seed(0)
+    model = get_latent_model(256, 8).to(DEV).eval()
+    for seed in range(2):
+        z = torch.randn(2, 4, 32, 32, device=DEV, generator=torch.Generator(device=DEV).manual_seed(seed))
+        got = bb.sample_latent_iadb(model, z, 3, "gaussianBN", 8, use_graph=True)
+        want = bb.sample_latent_iadb(model, z, 3, "gaussianBN", 8, use_graph=False)
+        assert torch.equal(got, want)
+    assert len(bs._sampler_cache) <= 4
