@@ -44,3 +44,16 @@ def to_uint8_nhwc(x: torch.Tensor) -> torch.Tensor:
         rc = _lib.load().bndm_to_uint8_nhwc(_lib.ptr(x), _lib.ptr(out), B, C, H, W, _lib.current_stream(x.device))
     _lib.check(rc, "bndm_to_uint8_nhwc")
     return out
+
+
+def iadb_snapshot_uint8(sample_chw: torch.Tensor, final: bool) -> np.ndarray:
+    """(C,H,W) fp32 -> (H,W,C) uint8 exactly as iadb_bn.py's test driver writes its PNGs (:796-802, :814-816):
+    the final image is ``clamp((x+1)/2, 0, 1)``, intermediate snapshots are min-max normalised, and the
+    conversion is ``(x*255).astype(uint8)`` -- a TRUNCATION, unlike ddim_diffusers.py:687-688 which rounds
+    (that variant is ``to_uint8_nhwc``).  Host-side convenience (plain torch ops, any device)."""
+    x = sample_chw
+    if final:
+        x = torch.clamp((x + 1) / 2.0, 0.0, 1.0)
+    else:
+        x = (x - x.min()) / (x.max() - x.min())
+    return (x.permute(1, 2, 0).detach().cpu().numpy() * 255).astype(np.uint8)

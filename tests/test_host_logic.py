@@ -218,3 +218,17 @@ def test_fused_unet_and_training_front_end_refuse_cpu():
         groupnorm_silu_nhwc(torch.randn(1, 128, 4, 4), torch.nn.GroupNorm(32, 128))
     with pytest.raises(bb.BndmError):
         bb.get_noise_train(torch.device("cpu"), torch.randn(2, 3, 64, 64), torch.eye(4096), torch.ones(2), torch.ones(2))
+
+
+def test_iadb_snapshot_uint8_follows_the_reference_driver():
+    """iadb_bn.py:796-802: clamp for the final image, min-max for snapshots, truncating uint8 cast."""
+    from bndm_b200.io import iadb_snapshot_uint8
+    torch.manual_seed(0)
+    x = torch.randn(3, 8, 8) * 0.7
+    fin = iadb_snapshot_uint8(x, final=True)
+    want = (torch.clamp((x + 1) / 2.0, 0.0, 1.0).permute(1, 2, 0).numpy() * 255).astype(np.uint8)
+    assert fin.dtype == np.uint8 and fin.shape == (8, 8, 3) and np.array_equal(fin, want)
+    snap = iadb_snapshot_uint8(x, final=False)
+    assert snap.min() == 0 and snap.max() == 255
+    # truncation, not rounding: 0.999 * 255 = 254.7 -> 254
+    assert iadb_snapshot_uint8(torch.full((1, 1, 1), 0.998), final=True)[0, 0, 0] == int((0.998 + 1) / 2 * 255)
