@@ -232,3 +232,23 @@ def test_iadb_snapshot_uint8_follows_the_reference_driver():
     assert snap.min() == 0 and snap.max() == 255
     # truncation, not rounding: 0.999 * 255 = 254.7 -> 254
     assert iadb_snapshot_uint8(torch.full((1, 1, 1), 0.998), final=True)[0, 0, 0] == int((0.998 + 1) / 2 * 255)
+
+
+def test_contraction_kernel_is_tcgen05_and_tma_in_sass():
+    """Static check on the shipped library: every gemm_tc_kernel instance issues tcgen05.mma (UTCHMMA), reads
+    TMEM (LDTM) and stages operands with bulk/tensor TMA (UBLKCP / UTMALDG); no legacy HMMA path anywhere."""
+    import shutil
+    import subprocess
+    import sys
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_evidence.py")],
+                         capture_output=True, text=True, check=True).stdout
+    blocks = [b for b in out.split("\n\n") if b.startswith("bndm::gemm_tc_kernel")]
+    assert len(blocks) >= 8
+    for b in blocks:
+        assert "UTCHMMA=" in b and "LDTM=" in b and ("UBLKCP=" in b or "UTMALDG=" in b), b
+        assert "STACK:0" in b, "register spill in the contraction kernel:\n" + b
+    assert "HMMA=" not in out.replace("UTCHMMA=", "")
