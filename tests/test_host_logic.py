@@ -252,3 +252,52 @@ def test_contraction_kernel_is_tcgen05_and_tma_in_sass():
         assert "UTCHMMA=" in b and "LDTM=" in b and ("UBLKCP=" in b or "UTMALDG=" in b), b
         assert "STACK:0" in b, "register spill in the contraction kernel:\n" + b
     assert "HMMA=" not in out.replace("UTCHMMA=", "")
+
+
+def test_c_abi_rejects_bad_arguments_before_touching_the_device():
+    """Argument validation of the C ABI (include/bndm_b200.h "Errors"): bad calls return a negative code and a
+    message through bndm_last_error() without launching anything, so this runs without a GPU.  The UNSUPPORTED
+    code is what the Python mirror turns into the reference's NotImplementedError (iadb_bn.py:331)."""
+    import ctypes as C
+    from bndm_b200 import _lib
+    lib = _lib.load()
+    fake = C.c_void_p(4096)                       # aligned, never dereferenced: every call below fails validation first
+
+    def err():
+        return lib.bndm_last_error().decode()
+
+    h = C.c_void_p()
+    assert lib.bndm_prepare_L(None, 4096, 12, None, C.byref(h)) == _lib.ERR_ARG and "null" in err()
+    assert lib.bndm_prepare_L(fake, 1024, 12, None, C.byref(h)) == _lib.ERR_UNSUPPORTED and "4096" in err()
+    assert lib.bndm_get_noise_f32(None, fake, None, fake, None, None, 4, 3, 64, 1, None) == _lib.ERR_ARG
+    assert lib.bndm_reserve_columns(None, 12, None) == _lib.ERR_ARG
+    assert lib.bndm_free_L(None) in (_lib.OK, _lib.ERR_ARG)
+    # IADB update: null pointers, bad shapes, channel count that the reference rejects, missing coefficient vectors
+    assert lib.bndm_iadb_step_f32(None, fake, fake, fake, None, 1, 3, 4096, 3, None) == _lib.ERR_ARG
+    assert lib.bndm_iadb_step_f32(fake, fake, fake, fake, None, 0, 3, 4096, 3, None) == _lib.ERR_ARG
+    assert lib.bndm_iadb_step_f32(fake, fake, fake, fake, fake, 1, 3, 4096, 5, None) == _lib.ERR_UNSUPPORTED
+    assert "5 channels" in err()
+    assert lib.bndm_iadb_step_f32(fake, fake, fake, fake, None, 1, 3, 4096, 6, None) == _lib.ERR_ARG
+    assert "coefficient" in err()
+    assert lib.bndm_iadb_step_sched_f32(fake, fake, fake, None, None, None, 1, 3, 4096, 6, None) == _lib.ERR_ARG
+    assert lib.bndm_iadb_step_sched_dnhwc_f32(fake, fake, fake, fake, None, None, 1, 3, 4096, 6, None) == _lib.ERR_ARG
+    assert lib.bndm_ddim_step_f32(fake, fake, None, None, None, None, None, 0, 0, 0, None) == _lib.ERR_ARG
+    # UNet glue kernels
+    assert lib.bndm_groupnorm_nhwc_f32(fake, None, 0, None, None, 0, fake, fake, None, fake, 1, 128, 16, 24,
+                                       1e-5, 1, None) == _lib.ERR_UNSUPPORTED      # 128 % 24 != 0
+    assert lib.bndm_groupnorm_nhwc_f32(fake, fake, 130, None, None, 0, fake, fake, None, fake, 1, 128, 16, 32,
+                                       1e-5, 1, None) == _lib.ERR_ARG              # second source wider than C
+    assert lib.bndm_groupnorm_nhwc_f32(C.c_void_p(4100), None, 0, None, None, 0, fake, fake, None, fake, 1, 128, 16, 32,
+                                       1e-5, 1, None) == _lib.ERR_ARG and "aligned" in err()
+    assert lib.bndm_add_bias_nhwc_f32(fake, None, None, fake, fake, fake, 130, 128, None) == _lib.ERR_ARG   # n % C
+    assert lib.bndm_upsample2x_nhwc_f32(fake, fake, 1, 4, 4, 6, None) == _lib.ERR_ARG                       # C % 4
+    assert lib.bndm_attention_small_f32(None, fake, 1, 16, 512, 8, None) == _lib.ERR_ARG
+    assert lib.bndm_to_uint8_nhwc(fake, None, 1, 3, 64, 64, None) == _lib.ERR_ARG
+    assert lib.bndm_white128_reinterpret_f32(fake, fake, 1, 3, None) == _lib.ERR_ARG and "in-place" in err()
+    # the mapping the Python mirror applies
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.ERR_UNSUPPORTED, "x")
+    with pytest.raises(ValueError):
+        _lib.check(_lib.ERR_ARG, "x")
+    with pytest.raises(_lib.BndmError):
+        _lib.check(_lib.ERR_CUDA, "x")
