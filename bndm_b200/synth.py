@@ -7,6 +7,7 @@ redistributable/offline, so benches and tests use:
                      hash (identical on every machine -> golden vectors stay valid);
 ``blue_noise_L``     Cholesky factor of a toroidal high-pass ("blue") covariance on the
                      64x64 tile -- spectrally like the paper's L (SURVEY.md section 8d);
+``empirical_covariance`` / ``cholesky_L``  covariance of sample fields -> L on the device (SURVEY N4);
 ``white_draw``       ``np.random.seed(s); np.random.randn(...)`` exactly as iadb_bn.py:75,761.
 """
 from __future__ import annotations
@@ -33,9 +34,9 @@ def hashed_tril(n: int = NPIX, seed: int = 0) -> np.ndarray:
     return np.tril(L).astype(np.float32)
 
 
-def blue_noise_L(fc: float = 0.35, p: float = 2.0, floor: float = 1e-3) -> np.ndarray:
-    """cholesky(Sigma) in float64 -> fp32, Sigma = circulant(IFFT2(S)), S(f) = max(floor,
-    min(1, |f|/fc)**p), unit diagonal.  (4096,4096) lower-triangular."""
+def blue_noise_sigma(fc: float = 0.35, p: float = 2.0, floor: float = 1e-3) -> np.ndarray:
+    """Toroidal high-pass covariance on the 64x64 tile, float64 (4096,4096), unit diagonal:
+    Sigma = circulant(IFFT2(S)), S(f) = max(floor, min(1, |f|/fc)**p)."""
     f = np.fft.fftfreq(TILE)
     fr = np.sqrt(f[:, None] ** 2 + f[None, :] ** 2)
     S = np.maximum(floor, np.minimum(1.0, fr / fc) ** p)
@@ -44,8 +45,34 @@ def blue_noise_L(fc: float = 0.35, p: float = 2.0, floor: float = 1e-3) -> np.nd
     yy, xx = np.divmod(np.arange(NPIX), TILE)
     dy = (yy[:, None] - yy[None, :]) % TILE
     dx = (xx[:, None] - xx[None, :]) % TILE
-    sigma = c[dy, dx]
-    return np.linalg.cholesky(sigma).astype(np.float32)
+    return c[dy, dx]
+
+
+def blue_noise_L(fc: float = 0.35, p: float = 2.0, floor: float = 1e-3) -> np.ndarray:
+    """cholesky(blue_noise_sigma(...)) in float64 -> fp32.  (4096,4096) lower-triangular."""
+    return np.linalg.cholesky(blue_noise_sigma(fc, p, floor)).astype(np.float32)
+
+
+def empirical_covariance(fields):
+    """(S, ...) samples of a random field (e.g. S blue-noise masks of 64x64, Gaussianised) -> (n,n) float64
+    covariance of the flattened, mean-removed fields, on the samples' device (torch).  The reference ships only
+    the finished factor (README.md:33); this and ``cholesky_L`` are the construction it leaves out."""
+    import torch
+    x = fields.reshape(fields.shape[0], -1).to(torch.float64)
+    x = x - x.mean(dim=0, keepdim=True)
+    return (x.T @ x) / max(x.shape[0] - 1, 1)
+
+
+def cholesky_L(cov, jitter: float = 0.0):
+    """Covariance (n,n) -> fp32 lower-triangular factor L with L @ L.T = cov (+ jitter * I), computed in float64
+    on cov's device (cuSOLVER potrf through torch on a GPU) -- the matrix ``get_noise_v2`` consumes as
+    ``cov_mat_L`` (iadb_bn.py:83-86).  Raises if cov is not positive definite (add jitter for empirical estimates
+    from fewer samples than pixels)."""
+    import torch
+    c = cov.to(torch.float64)
+    if jitter:
+        c = c + jitter * torch.eye(c.shape[0], dtype=torch.float64, device=c.device)
+    return torch.linalg.cholesky(c).to(torch.float32)
 
 
 def white_draw(shape, seed: int = 0) -> np.ndarray:

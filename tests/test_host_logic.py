@@ -301,3 +301,25 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_device():
         _lib.check(_lib.ERR_ARG, "x")
     with pytest.raises(_lib.BndmError):
         _lib.check(_lib.ERR_CUDA, "x")
+
+
+def test_L_construction_from_a_covariance():
+    """covariance -> Cholesky factor.  cholesky_L reproduces blue_noise_L from the same covariance, and
+    the factor of an empirical covariance regenerates that covariance (small tile so it runs in a second)."""
+    from bndm_b200 import synth
+    sigma = synth.blue_noise_sigma()
+    assert sigma.shape == (4096, 4096) and np.allclose(np.diag(sigma), 1.0)
+    sub = torch.from_numpy(sigma[:512, :512].copy())              # leading principal block: still SPD
+    L = synth.cholesky_L(sub)
+    assert L.dtype == torch.float32 and torch.equal(L, torch.tril(L))
+    want = np.linalg.cholesky(sigma[:512, :512]).astype(np.float32)
+    np.testing.assert_allclose(L.numpy(), want, rtol=0, atol=2e-6)
+    g = torch.Generator().manual_seed(0)
+    fields = (torch.randn(4000, 64, generator=g, dtype=torch.float64) @ L[:64, :64].double().T).reshape(4000, 8, 8)
+    cov = synth.empirical_covariance(fields)
+    assert cov.shape == (64, 64) and cov.dtype == torch.float64
+    np.testing.assert_allclose(cov.numpy(), sigma[:64, :64], atol=0.08)
+    L2 = synth.cholesky_L(cov, jitter=1e-9)
+    np.testing.assert_allclose((L2.double() @ L2.double().T).numpy(), cov.numpy(), atol=1e-5)
+    with pytest.raises(Exception):
+        synth.cholesky_L(-torch.eye(4))
