@@ -16,6 +16,12 @@ $(LIB): $(OBJ)
 	@mkdir -p bndm_b200/lib
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
 
+# stand-alone measurement probes (not part of the library): `make probes` here, then run build/<probe> under gpurun
+probes: build/stream_probe
+build/stream_probe: tools/probes/stream_probe.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -o $@ $<
+
 clean:
 	rm -rf build $(LIB)
-.PHONY: all clean
+.PHONY: all clean probes
