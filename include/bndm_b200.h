@@ -150,7 +150,7 @@ int bndm_ddim_step_f32(float *x_out, const float *x, const float *eps, const flo
 
 /* Debug / test hook: force the contraction's variants (-1 = default rule, 0 = off, 1 = on):
  * fused_combine = the last CTA of a row tile sums its partial tiles inside the contraction
- * (default: column blocks <= 32); raw_L = raw fp32 L blocks + in-kernel lo conversion (default:
+ * (default: off -- slower than the separate combine launch); raw_L = raw fp32 L blocks + in-kernel lo conversion (default:
  * one column block of <= 64 columns).  Process-wide.                                         */
 int bndm_debug_set_policy(int fused_combine, int raw_L);
 
