@@ -2,7 +2,7 @@
 // costs ~20 s of box time instead of minutes).  Links libbndm_b200.so; variants are chosen with the library's
 // env knobs (BNDM_TC_STAGES, BNDM_TC_FUSED, BNDM_TC_RAWL, BNDM_TC_SUB, BNDM_TC_MAX_NB, BNDM_NO_PDL ...).
 //
-//   make probes && build/get_noise_probe [B=4] [C=3] [reps=9]
+//   make probes && build/get_noise_probe [B=4] [C=3] [reps=9] [clean_flush=0]
 //
 // Prints: max |error| of out / bn / wn against an fp64 host evaluation of  bn = L z,  out = bn (1-g) + z g
 // (64x64 branch, BNDM_SRC_IMAGE), the cold whole-call time (graph of 10 x [L2 flush, call] minus the flushes),
@@ -43,13 +43,22 @@ static inline uint32_t rnd() {
 static inline double uni() { return (rnd() + 0.5) / 2147483648.0; }
 static inline float gauss() { return (float)(sqrt(-2.0 * log(uni())) * cos(6.283185307179586 * uni())); }
 
-__global__ void flush_kernel(float4 *buf, size_t n) {
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ float g_sink;
+__global__ void flush_kernel(float4 *buf, size_t n, int clean) {      // clean: flush with reads (no dirty lines left)
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (clean) acc += buf[i].x;
+    else buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (clean && acc == 12345.678f) g_sink = acc;
 }
+// one tiny grid between the flush and the call: the contraction is launched with programmatic stream
+// serialisation and would otherwise start (and stamp its trace) while the flush is still draining
+__global__ void spacer_kernel() {}
 
 int main(int argc, char **argv) {
   const int B = argc > 1 ? atoi(argv[1]) : 4, C = argc > 2 ? atoi(argv[2]) : 3, reps = argc > 3 ? atoi(argv[3]) : 9;
+  const int clean = argc > 4 ? atoi(argv[4]) : 0;
   const int n = 4096, N = B * C;
   const size_t img = (size_t)N * n;
   printf("# get_noise probe: B=%d C=%d (N=%d columns), 64x64, gaussianBN, inplace; sm100=%d\n", B, C, N, bndm_device_is_sm100());
@@ -117,7 +126,8 @@ int main(int argc, char **argv) {
     cudaGraphExec_t ge;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < 10; ++i) {
-      flush_kernel<<<148 * 4, 512, 0, st>>>(dflush, flush_bytes / 16);
+      flush_kernel<<<148 * 4, 512, 0, st>>>(dflush, flush_bytes / 16, clean);
+      spacer_kernel<<<1, 32, 0, st>>>();
       if (with_call) CB(bndm_get_noise_f32(h, dz, dg, dout, nullptr, nullptr, B, C, 64, BNDM_SRC_IMAGE, st));
     }
     CK(cudaStreamEndCapture(st, &g));
@@ -145,14 +155,15 @@ int main(int argc, char **argv) {
   const float t_call = time_graph(g_call), t_flush = time_graph(g_flush);
   const double us = (t_call - t_flush) * 100.0;
   const double bytes = 4.0 * n * (n + 1) / 2 + 4.0 * img * 2;       // L triangle + z read + out written
-  printf("cold whole call (1 output): %.2f us  => %.2f TB/s algorithmic (%.1f MB)\n", us, bytes / us * 1e-6, bytes * 1e-6);
+  printf("cold whole call (1 output, %s flush): %.2f us  => %.2f TB/s algorithmic (%.1f MB)\n", clean ? "clean" : "dirty", us, bytes / us * 1e-6, bytes * 1e-6);
 
   // ---- per-CTA timeline of the contraction kernel
   CB(bndm_debug_set_trace(h, dtrace));
   std::vector<unsigned long long> tr(148 * 24);
   for (int it = 0; it < 3; ++it) {
-    flush_kernel<<<148 * 4, 512, 0, st>>>(dflush, flush_bytes / 16);
+    flush_kernel<<<148 * 4, 512, 0, st>>>(dflush, flush_bytes / 16, clean);
     CK(cudaMemsetAsync(dtrace, 0, 148 * 24 * 8, st));
+    spacer_kernel<<<1, 32, 0, st>>>();
     CB(bndm_get_noise_f32(h, dz, dg, dout, nullptr, nullptr, B, C, 64, BNDM_SRC_IMAGE, st));
     CK(cudaStreamSynchronize(st));
   }

@@ -2,7 +2,7 @@
 // (profiles/r01_experiment_log.md, "Round-2 work plan").  Not part of libbndm_b200.so.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o build/stream_probe tools/probes/stream_probe.cu
-//   build/stream_probe            # prints one line per configuration
+//   build/stream_probe [reps=7] [clean=0]     # prints one line per configuration; clean=1 flushes L2 with reads
 //
 // (1) tma   : G persistent CTAs each stream a contiguous slice of a 33.5 MB buffer (= the lower triangle of L)
 //             with linear cp.async.bulk requests of `req` bytes, `depth` in flight, data not consumed: the
@@ -126,9 +126,15 @@ __global__ void __launch_bounds__(512) ldg_stream_kernel(const float4 *src, size
   if (threadIdx.x == 0) st[blockIdx.x] = Stamps{t0, t_first, gtime(), 0, 0};
 }
 
-__global__ void flush_kernel(float4 *buf, size_t n) {              // dirties > L2 worth of lines
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+__global__ void flush_kernel(float4 *buf, size_t n, int clean, float *sink) {
+  // clean == 0: dirties > L2 worth of lines (their write-backs then share the DRAM bus with the probe's reads);
+  // clean == 1: reads them instead, leaving clean lines that are dropped without traffic
+  float acc = 0.f;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (clean) acc += buf[i].x;
+    else buf[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (clean && acc == 12345.678f) sink[1] = acc;
 }
 
 struct Result {
@@ -156,10 +162,12 @@ static Result reduce(const std::vector<Stamps> &s, bool fence) {
 int main(int argc, char **argv) {
   const size_t total = 33562624 / (148 * 65536) * (size_t)(148 * 65536) + 148 * 65536;     // ~33.5 MB, divisible for every config
   const int reps = argc > 1 ? atoi(argv[1]) : 7;
+  const int clean = argc > 2 ? atoi(argv[2]) : 0;                    // 1: flush L2 with reads (clean lines)
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
-  printf("# device %s, %d SMs, buffer %.2f MB, %d cold repetitions (median)\n", prop.name, sms, total * 1e-6, reps);
+  printf("# device %s, %d SMs, buffer %.2f MB, %d cold repetitions (median), L2 flushed with %s\n", prop.name, sms, total * 1e-6, reps,
+         clean ? "reads (clean lines)" : "writes (dirty lines)");
   char *src;
   float4 *flush;
   float *partials, *sink;
@@ -182,7 +190,7 @@ int main(int argc, char **argv) {
     size_t per = total / G;
     if (req) per = per / req * req;
     for (int r = 0; r < reps + 1; ++r) {
-      flush_kernel<<<sms * 4, 512>>>(flush, flush_bytes / 16);
+      flush_kernel<<<sms * 4, 512>>>(flush, flush_bytes / 16, clean, sink);
       if (req)
         tma_stream_kernel<<<G, 128, (size_t)req * depth>>>(src, per, req, depth, partials, counter, fence, st_dev);
       else
