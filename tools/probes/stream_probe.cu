@@ -10,6 +10,8 @@
 // (2) ldg   : the same slice with 128-bit ld.global.nc from all threads (what a SIMT kernel would see).
 // (3) fence : after streaming, every CTA stores an 8 KiB partial tile, __threadfence()s and bumps a counter
 //             (the hand-off the in-kernel combine needs): how long does the fence take while others still stream?
+// (4) hold  : (1) with a consumer that keeps each landed stage for 300 / 600 ns of serial work, at several ring depths
+//             and with cp.async.bulk.prefetch.L2 look-ahead: isolates why deeper rings / look-ahead lost inside K1b.
 // Times are %globaltimer stamps taken in the kernel: span = max(end) - min(start) over CTAs.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -68,8 +70,14 @@ constexpr int kMaxDepth = 8;
 
 // (1) + (3): thread 0 is producer and consumer at once: it keeps `depth` requests in flight and re-arms a slot
 // as soon as its bytes have landed.  Nothing reads the data: this is the TMA/DRAM ceiling.
+// hold_ns > 0 emulates a consumer that keeps a landed stage for that long before the slot is re-armed (K1b: ~1200 ns
+// for conversion + MMA issue + completion); ahead > 0 keeps that many requests beyond the ring prefetched into L2.
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __global__ void __launch_bounds__(128) tma_stream_kernel(const char *src, size_t bytes_per_cta, uint32_t req, int depth,
-                                                         float *partials, unsigned *counter, int do_fence, Stamps *st) {
+                                                         float *partials, unsigned *counter, int do_fence, int hold_ns,
+                                                         int ahead, Stamps *st) {
   extern __shared__ __align__(1024) char smem[];
   __shared__ uint64_t full[kMaxDepth];
   const char *mine = src + (size_t)blockIdx.x * bytes_per_cta;
@@ -83,11 +91,19 @@ __global__ void __launch_bounds__(128) tma_stream_kernel(const char *src, size_t
       mbar_expect_tx(&full[i], req);
       bulk_load(smem_u32(smem + (size_t)i * req), mine + (size_t)i * req, req, &full[i]);
     }
+    for (int i = depth; i < depth + ahead && i < n_req; ++i) bulk_prefetch_l2(mine + (size_t)i * req, req);
+    uint64_t busy_until = 0;                       // the emulated consumer handles one stage at a time
     for (int i = 0; i < n_req; ++i) {
       const int slot = i % depth;
       mbar_wait(&full[slot], (i / depth) & 1);
       if (i == 0) t_first = gtime();
+      if (hold_ns > 0) {
+        const uint64_t now = gtime();
+        busy_until = (now > busy_until ? now : busy_until) + (uint64_t)hold_ns;
+        while (gtime() < busy_until) {}
+      }
       const int nxt = i + depth;
+      if (ahead > 0 && nxt + ahead < n_req) bulk_prefetch_l2(mine + (size_t)(nxt + ahead) * req, req);
       if (nxt < n_req) {
         mbar_expect_tx(&full[slot], req);
         bulk_load(smem_u32(smem + (size_t)slot * req), mine + (size_t)nxt * req, req, &full[slot]);
@@ -184,7 +200,7 @@ int main(int argc, char **argv) {
   CK(cudaMalloc(&st_dev, 4 * sms * sizeof(Stamps)));
   CK(cudaFuncSetAttribute(tma_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 
-  auto run = [&](const char *name, int G, uint32_t req, int depth, int fence, int threads) {
+  auto run = [&](const char *name, int G, uint32_t req, int depth, int fence, int threads, int hold_ns = 0, int ahead = 0) {
     std::vector<double> span, first, firstmin, fmean, fmax;
     std::vector<Stamps> st(G);
     size_t per = total / G;
@@ -192,7 +208,7 @@ int main(int argc, char **argv) {
     for (int r = 0; r < reps + 1; ++r) {
       flush_kernel<<<sms * 4, 512>>>(flush, flush_bytes / 16, clean, sink);
       if (req)
-        tma_stream_kernel<<<G, 128, (size_t)req * depth>>>(src, per, req, depth, partials, counter, fence, st_dev);
+        tma_stream_kernel<<<G, 128, (size_t)req * depth>>>(src, per, req, depth, partials, counter, fence, hold_ns, ahead, st_dev);
       else
         ldg_stream_kernel<<<G, threads>>>(reinterpret_cast<const float4 *>(src), per / 16, sink, st_dev);
       CK(cudaGetLastError());
@@ -214,6 +230,7 @@ int main(int argc, char **argv) {
     printf("%-5s G=%3d req=%3uK depth=%d thr=%4d | span %6.2f us  %5.2f TB/s | first data mean %5.2f min %5.2f us", name, G,
            req >> 10, depth, threads, med(span), bytes / med(span) * 1e-6, med(first), med(firstmin));
     if (fence) printf(" | store+fence+atomic mean %5.2f max %5.2f us", med(fmean), med(fmax));
+    if (hold_ns || ahead) printf(" | consumer holds a stage %d ns, L2 look-ahead %d requests", hold_ns, ahead);
     printf("\n");
   };
 
@@ -224,6 +241,11 @@ int main(int argc, char **argv) {
   run("tma", 2 * sms, 32u << 10, 3, 0, 128);
   run("tma", sms, 32u << 10, 3, 1, 128);
   run("tma", sms, 32u << 10, 4, 1, 128);
+  // a consumer that holds every stage (K1b: conversion + MMA issue + completion ~ 600 ns serial work per 32 KiB stage,
+  // the slot is free ~1200 ns after landing): how much ring depth / L2 look-ahead does the stream need then?
+  for (int hold : {300, 600})
+    for (int depth : {3, 4, 5, 6}) run("tma", sms, 32u << 10, depth, 0, 128, hold, 0);
+  for (int ahead : {2, 4, 8}) run("tma", sms, 32u << 10, 3, 0, 128, 600, ahead);
   for (int threads : {256, 512})
     for (int mult : {1, 2, 4}) run("ldg", mult * sms, 0, 0, 0, threads);
   return 0;
