@@ -14,7 +14,7 @@ echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== bench (ours)"; timeout 1200 python bench.py > $OUT/bench.json 2> $OUT/bench.err; tail -c 1500 $OUT/bench.json; tail -5 $OUT/bench.err
 echo "== bench (reference arm)"; timeout 900 python bench.py --impl reference > $OUT/bench_reference.json 2> $OUT/bench_reference.err; tail -c 600 $OUT/bench_reference.json
 if [ -x build/stream_probe ]; then echo "== stream probe (make probes)"; (timeout 120 build/stream_probe 7 0; timeout 120 build/stream_probe 7 1) > $OUT/stream_probe.txt 2>&1; tail -60 $OUT/stream_probe.txt; fi
-if [ -x build/get_noise_probe ]; then (timeout 60 build/get_noise_probe 4 3 9 0; timeout 60 build/get_noise_probe 4 3 9 1; timeout 60 build/get_noise_probe 64 3 9 1) > $OUT/get_noise_probe.txt 2>&1; grep -E "^#|parity|cold|span" $OUT/get_noise_probe.txt; fi
+if [ -x build/get_noise_probe ]; then (timeout 60 build/get_noise_probe 4 3 9 0; timeout 60 build/get_noise_probe 4 3 9 1; timeout 60 build/get_noise_probe 4 3 9 2; timeout 60 build/get_noise_probe 64 3 9 1) > $OUT/get_noise_probe.txt 2>&1; grep -E "^#|parity|whole call|span" $OUT/get_noise_probe.txt; fi
 if [ -z "$SKIP_NCU" ]; then
 echo "== ncu launch list (bench.py, 1 warm-up + 1 timed sampling step of 1 denoising step per arm)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $OUT/launches.csv \

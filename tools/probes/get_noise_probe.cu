@@ -2,7 +2,7 @@
 // costs ~20 s of box time instead of minutes).  Links libbndm_b200.so; variants are chosen with the library's
 // env knobs (BNDM_TC_STAGES, BNDM_TC_FUSED, BNDM_TC_RAWL, BNDM_TC_SUB, BNDM_TC_MAX_NB, BNDM_NO_PDL ...).
 //
-//   make probes && build/get_noise_probe [B=4] [C=3] [reps=9] [clean_flush=0]
+//   make probes && build/get_noise_probe [B=4] [C=3] [reps=9] [flush=0]   (0: write flush, 1: read flush, 2: none = L2-warm)
 //
 // Prints: max |error| of out / bn / wn against an fp64 host evaluation of  bn = L z,  out = bn (1-g) + z g
 // (64x64 branch, BNDM_SRC_IMAGE), the cold whole-call time (graph of 10 x [L2 flush, call] minus the flushes),
@@ -126,7 +126,7 @@ int main(int argc, char **argv) {
     cudaGraphExec_t ge;
     CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < 10; ++i) {
-      flush_kernel<<<148 * 4, 512, 0, st>>>(dflush, flush_bytes / 16, clean);
+      if (clean != 2) flush_kernel<<<148 * 4, 512, 0, st>>>(dflush, flush_bytes / 16, clean);
       spacer_kernel<<<1, 32, 0, st>>>();
       if (with_call) CB(bndm_get_noise_f32(h, dz, dg, dout, nullptr, nullptr, B, C, 64, BNDM_SRC_IMAGE, st));
     }
@@ -155,13 +155,13 @@ int main(int argc, char **argv) {
   const float t_call = time_graph(g_call), t_flush = time_graph(g_flush);
   const double us = (t_call - t_flush) * 100.0;
   const double bytes = 4.0 * n * (n + 1) / 2 + 4.0 * img * 2;       // L triangle + z read + out written
-  printf("cold whole call (1 output, %s flush): %.2f us  => %.2f TB/s algorithmic (%.1f MB)\n", clean ? "clean" : "dirty", us, bytes / us * 1e-6, bytes * 1e-6);
+  printf("whole call (1 output, %s flush): %.2f us  => %.2f TB/s algorithmic (%.1f MB)\n", clean == 2 ? "no (L2-warm)" : clean ? "clean" : "dirty", us, bytes / us * 1e-6, bytes * 1e-6);
 
   // ---- per-CTA timeline of the contraction kernel
   CB(bndm_debug_set_trace(h, dtrace));
   std::vector<unsigned long long> tr(148 * 24);
   for (int it = 0; it < 3; ++it) {
-    flush_kernel<<<148 * 4, 512, 0, st>>>(dflush, flush_bytes / 16, clean);
+    if (clean != 2) flush_kernel<<<148 * 4, 512, 0, st>>>(dflush, flush_bytes / 16, clean);
     CK(cudaMemsetAsync(dtrace, 0, 148 * 24 * 8, st));
     spacer_kernel<<<1, 32, 0, st>>>();
     CB(bndm_get_noise_f32(h, dz, dg, dout, nullptr, nullptr, B, C, 64, BNDM_SRC_IMAGE, st));
