@@ -17,11 +17,15 @@ $(LIB): $(OBJ)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
 
 # stand-alone measurement probes (not part of the library): `make probes` here, then run build/<probe> under gpurun
-probes: build/stream_probe build/get_noise_probe
+probes: build/stream_probe build/get_noise_probe build/pipe_probe
 build/get_noise_probe: tools/probes/get_noise_probe.cu $(LIB) include/bndm_b200.h
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -std=c++17 -o $@ $< -Lbndm_b200/lib -lbndm_b200 -Xlinker -rpath -Xlinker '$$ORIGIN/../bndm_b200/lib'
 build/stream_probe: tools/probes/stream_probe.cu
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -o $@ $<
+
+build/pipe_probe: tools/probes/pipe_probe.cu
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -lineinfo -std=c++17 -o $@ $<
 

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libbndm_b200.so")
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE, ERR_ARCH = 0, -1, -2, -3, -4, -5
 
 SRC_DRAW, SRC_IMAGE = 0, 1
-GEMM_TC, GEMM_SIMT, FORCE_DENSE = 0, 16, 32
+GEMM_AUTO, GEMM_SIMT, FORCE_DENSE, GEMM_GEMV, GEMM_TC = 0, 16, 32, 64, 128
 
 # name -> (restype, argtypes); mirrors include/bndm_b200.h one to one
 _P = C.c_void_p
@@ -32,8 +32,10 @@ SIGNATURES = {
     "bndm_profile_enable": (C.c_int, [_P, C.c_int]),
     "bndm_profile_last_ms": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "bndm_get_noise_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_uint, _P]),
+    "bndm_get_noise_shard_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, _P]),
     "bndm_get_noise_train_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_uint, _P]),
     "bndm_white128_reinterpret_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "bndm_white128_reinterpret_shard_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_iadb_step_f32": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_iadb_step_sched_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_iadb_step_sched_dnhwc_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
@@ -42,6 +44,7 @@ SIGNATURES = {
     "bndm_debug_set_policy": (C.c_int, [C.c_int, C.c_int]),
     "bndm_debug_streamk_check": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "bndm_debug_streamk_check_sub": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "bndm_debug_gemv_schedule_check": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bndm_groupnorm_nhwc_f32": (C.c_int, [_P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.c_float, C.c_int, _P]),
     "bndm_upsample2x_nhwc_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),

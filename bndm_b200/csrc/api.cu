@@ -20,7 +20,9 @@ void set_error(const char *fmt, ...) {
 }
 
 static int fail_cuda(cudaError_t e, const char *what) {
-  set_error("%s: %s", what, cudaGetErrorString(e));
+  char detail[256];
+  snprintf(detail, sizeof(detail), "%s", g_err);          // a launcher may have left the precise reason
+  set_error("%s: %s%s%s", what, cudaGetErrorString(e), detail[0] ? " -- " : "", detail);
   return BNDM_ERR_CUDA;
 }
 
@@ -68,7 +70,11 @@ struct bndm_L {
   int *tile_counters = nullptr;   // owned: kMaxTileCounters ints, zero between calls (fused combine)
   int64_t ws_bytes = 0;
   // optional per-launch timing (bndm_profile_enable)
-  unsigned long long *trace = nullptr;   // debug: per-CTA time stamps of the tcgen05 kernel (caller-owned)
+  int *gv_sched[4] = {nullptr, nullptr, nullptr, nullptr};   // owned: K1g row schedules [2 res32 + dense] -> [n_sms][kGemvTableStride]
+  float *gv_L[4] = {nullptr, nullptr, nullptr, nullptr};     // owned: L in the stream order of that schedule
+  int gv_variant = 0;
+  int n_sms = 148;
+  unsigned long long *trace = nullptr;   // debug: per-CTA time stamps of the contraction kernel (caller-owned)
   int profile = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int ev_valid = 0;
@@ -150,6 +156,29 @@ static int alloc_ws(bndm_L *h, int max_columns) {
   return BNDM_OK;
 }
 
+// K1g set-up for table k = 2 res32 + dense: host row schedule -> device, then L gathered into stream order.
+// Leaves gv_sched[k] null (K1g unavailable, K1b takes over) when the quads do not fit the device's SMs.
+static int gv_build(bndm_L *h, int k, cudaStream_t s) {
+  if (h->gv_sched[k]) return BNDM_OK;
+  const size_t n = (size_t)h->n_sms * kGemvTableStride;
+  int *host = new (std::nothrow) int[n];
+  if (!host) { set_error("out of host memory"); return BNDM_ERR_ARG; }
+  const long blocks = gemv_build_schedule(k >> 1, k & 1, h->n_sms, h->gv_variant, host);
+  if (blocks < 0) { delete[] host; return BNDM_OK; }
+  int *sched = nullptr;
+  float *Lg = nullptr;
+  cudaError_t e = cudaMalloc(&sched, n * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&Lg, (size_t)blocks * 4 * gemv_kw(h->gv_variant) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(sched, host, n * sizeof(int), cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = launch_gemv_pack_L(h->L, Lg, sched, h->n_sms, h->gv_variant, k & 1, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  delete[] host;
+  if (e != cudaSuccess) { cudaFree(sched); cudaFree(Lg); return fail_cuda(e, "K1g schedule / stream-ordered L"); }
+  h->gv_sched[k] = sched;
+  h->gv_L[k] = Lg;
+  return BNDM_OK;
+}
+
 extern "C" {
 
 int bndm_version(void) { return BNDM_ABI_VERSION; }
@@ -194,6 +223,19 @@ int bndm_prepare_L(const float *L_dev, int n, int max_columns, void *stream, bnd
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) { bndm_free_L(h); return fail_cuda(e, "tf32 split / tiling of L"); }
+  }
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || h->n_sms < 1)
+      h->n_sms = 148;
+    h->gv_variant = gemv_variant();
+    // K1g: row schedule + stream-ordered copy of L for the 64^2/128^2 and the 32^2 row sets (the dense walk of a
+    // triangular L is a testing path, built on first use)
+    if (h->sm100)
+      for (int res32 = 0; res32 < 2; ++res32) {
+        int rc = gv_build(h, 2 * res32 + (h->lower_triangular ? 0 : 1), s);
+        if (rc != BNDM_OK) { bndm_free_L(h); return rc; }
+      }
   }
   int rc = alloc_ws(h, max_columns);
   if (rc != BNDM_OK) { bndm_free_L(h); return rc; }
@@ -257,6 +299,7 @@ int bndm_free_L(bndm_L *h) {
   cudaFree(h->Lt_dense);
   cudaFree(h->Lr);
   cudaFree(h->tile_counters);
+  for (int k = 0; k < 4; ++k) { cudaFree(h->gv_sched[k]); cudaFree(h->gv_L[k]); }
   delete h;
   return BNDM_OK;
 }
@@ -264,9 +307,12 @@ int bndm_free_L(bndm_L *h) {
 }  // extern "C"
 
 static int get_noise_impl(bndm_L *h, const float *z, const float *gamma, float *out, float *out_bn, float *out_wn, int B,
-                          int C, int res, unsigned flags, void *stream, const TrainOut &train) {
+                          int C, int res, unsigned flags, void *stream, const TrainOut &train, int Bg = 0, int b0 = 0) {
+  g_err[0] = 0;
   if (!h || !z || (!out && !train.x_alpha)) { set_error("bndm_get_noise_f32: null argument"); return BNDM_ERR_ARG; }
   if (B < 1 || C < 1) { set_error("bndm_get_noise_f32: bad shape B=%d C=%d", B, C); return BNDM_ERR_ARG; }
+  if (Bg == 0) Bg = B;                       // not sharded
+  if (b0 < 0 || b0 + B > Bg) { set_error("bndm_get_noise_shard_f32: shard [%d, %d) outside the global batch %d", b0, b0 + B, Bg); return BNDM_ERR_ARG; }
   int mode;
   if (res == 64) mode = kRes64;
   else if (res == 32) mode = kRes32;
@@ -274,11 +320,88 @@ static int get_noise_impl(bndm_L *h, const float *z, const float *gamma, float *
   else { set_error("bndm_get_noise_f32: resolution %d not implemented (32/64/128)", res); return BNDM_ERR_UNSUPPORTED; }
   cudaStream_t s = (cudaStream_t)stream;
   const int src_is_image = (flags & BNDM_SRC_IMAGE) ? 1 : 0;
+  // Sharded call: z is the GLOBAL white field.  Only the 128^2 image source couples samples across the batch
+  // (tile n = k*Bg + b is re-read as (b', k') = divmod(n, 4), get_noise_recent.py:131-146): there the gather kernel
+  // works on global tile indices; everywhere else a shard's columns are a contiguous slice of the global ones.
+  if (!(mode == kRes128 && src_is_image))
+    z += (int64_t)b0 * C * (mode == kRes128 ? 4 * kNPix : (src_is_image && mode == kRes32) ? 1024 : kNPix);
   const bool simt = (flags & BNDM_GEMM_SIMT) != 0;
-  if (!simt && !h->sm100) { set_error("tcgen05 path needs an sm_100 device"); return BNDM_ERR_ARCH; }
+  if (!simt && !h->sm100) { set_error("the tcgen05 / TMA paths need an sm_100 device"); return BNDM_ERR_ARCH; }
   const int dense = (!h->lower_triangular || (flags & BNDM_FORCE_DENSE)) ? 1 : 0;
 
   const int n_cols = B * C * (mode == kRes128 ? 4 : 1);
+  // K1g (streaming fp32 kernel, one launch, no split-K) in the GEMV regime; K1b (tcgen05) above it
+  const int gv_table = (mode == kRes32 ? 2 : 0) + dense;
+  bool gemv = false;
+  if (dense && h->lower_triangular && h->sm100 && !h->gv_sched[gv_table] && !simt && !(flags & BNDM_GEMM_TC) && n_cols <= kGemvMaxCols &&
+      !stream_is_capturing(s)) {
+    int rc = gv_build(h, gv_table, s);             // BNDM_FORCE_DENSE on a triangular L (testing): built once
+    if (rc != BNDM_OK) return rc;
+  }
+  if (flags & BNDM_GEMM_GEMV) {
+    if (simt || (flags & BNDM_GEMM_TC)) { set_error("bndm_get_noise_f32: conflicting kernel flags"); return BNDM_ERR_ARG; }
+    if (n_cols > kGemvMaxCols || !h->gv_sched[gv_table]) {
+      set_error("BNDM_GEMM_GEMV: %d columns (max %d)", n_cols, kGemvMaxCols);
+      return BNDM_ERR_UNSUPPORTED;
+    }
+    gemv = true;
+  } else if (!simt && !(flags & BNDM_GEMM_TC)) {
+    gemv = n_cols <= kGemvAutoCols && h->gv_sched[gv_table] != nullptr && gemv_policy();
+  }
+  if (gemv) {
+    // white columns: the caller's tensor unless they must be gathered from an image (32^2 tiling, 128^2 quadrants)
+    const bool gather = src_is_image && mode != kRes64;
+    const int nbg = tc_pick_nb(n_cols);
+    const int n_cols_pad_g = (n_cols + nbg - 1) / nbg * nbg;
+    if (gather && n_cols_pad_g > h->cap_cols) {
+      int rc = bndm_reserve_columns(h, n_cols, stream);
+      if (rc != BNDM_OK) return rc;
+    }
+    if ((reinterpret_cast<uintptr_t>(z) % 16) != 0) { set_error("bndm_get_noise_f32: z must be 16-byte aligned"); return BNDM_ERR_ARG; }
+    const bool prof = h->profile && !stream_is_capturing(s);
+    if (prof) CK(cudaEventRecord(h->ev[0], s));
+    if (gather) {
+      PackArgs p;
+      p.src = z;
+      p.z_raw = h->z_raw;
+      p.zt = nullptr;
+      p.nb = nbg;
+      p.n_cols = n_cols;
+      p.n_cols_pad = n_cols_pad_g;
+      p.B = B;
+      p.C = C;
+      p.res_mode = mode;
+      p.src_is_image = src_is_image;
+      p.Bg = Bg;
+      p.n0 = 4 * b0;
+      CK(launch_pack(p, s));
+    }
+    if (prof) CK(cudaEventRecord(h->ev[1], s));
+    GemvArgs g;
+    g.Lg = h->gv_L[gv_table];
+    g.z_cols = gather ? h->z_raw : z;
+    g.sched = h->gv_sched[gv_table];
+    g.n_ctas = h->n_sms;
+    g.dense = dense;
+    g.variant = h->gv_variant;
+    g.gamma = gamma;
+    g.out = out;
+    g.out_bn = out_bn;
+    g.out_wn = out_wn;
+    g.n_cols = n_cols;
+    g.B = B;
+    g.C = C;
+    g.res_mode = mode;
+    g.train = train;
+    g.trace = h->trace;
+    CK(launch_gemv(g, s));
+    if (prof) {
+      CK(cudaEventRecord(h->ev[2], s));
+      CK(cudaEventRecord(h->ev[3], s));
+      h->ev_valid = 1;
+    }
+    return BNDM_OK;
+  }
   const int nb = tc_pick_nb(n_cols);
   const int n_cols_pad = (n_cols + nb - 1) / nb * nb;
   const int n_row_tiles = mode == kRes32 ? kNumBlk / 2 : kNumBlk;
@@ -312,6 +435,8 @@ static int get_noise_impl(bndm_L *h, const float *z, const float *gamma, float *
   p.C = C;
   p.res_mode = mode;
   p.src_is_image = src_is_image;
+  p.Bg = Bg;
+  p.n0 = 4 * b0;
   const bool prof = h->profile && !stream_is_capturing(s);
   if (prof) CK(cudaEventRecord(h->ev[0], s));
   if (p.z_raw || p.zt) CK(launch_pack(p, s));
@@ -430,10 +555,23 @@ int bndm_get_noise_train_f32(bndm_L *h, const float *z, const float *gamma, cons
                         TrainOut{x1, alpha, alpha_prev, x_alpha, tar1, tar2});
 }
 
+int bndm_get_noise_shard_f32(bndm_L *h, const float *z_global, const float *gamma, float *out, float *out_bn, float *out_wn,
+                             int B, int C, int res, unsigned flags, int B_global, int b_offset, void *stream) {
+  if (!out) { set_error("bndm_get_noise_shard_f32: null argument"); return BNDM_ERR_ARG; }
+  if (B_global < 1) { set_error("bndm_get_noise_shard_f32: bad global batch %d", B_global); return BNDM_ERR_ARG; }
+  return get_noise_impl(h, z_global, gamma, out, out_bn, out_wn, B, C, res, flags, stream,
+                        TrainOut{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, B_global, b_offset);
+}
+
 int bndm_white128_reinterpret_f32(const float *x, float *out, int B, int C, void *stream) {
-  if (!x || !out || B < 1 || C < 1) { set_error("bndm_white128_reinterpret_f32: bad argument"); return BNDM_ERR_ARG; }
-  if (x == out) { set_error("bndm_white128_reinterpret_f32: in-place not supported"); return BNDM_ERR_ARG; }
-  CK(launch_white128(x, out, B, C, (cudaStream_t)stream));
+  return bndm_white128_reinterpret_shard_f32(x, out, B, C, B, 0, stream);
+}
+
+int bndm_white128_reinterpret_shard_f32(const float *x_global, float *out, int B, int C, int B_global, int b_offset, void *stream) {
+  if (!x_global || !out || B < 1 || C < 1) { set_error("bndm_white128_reinterpret_f32: bad argument"); return BNDM_ERR_ARG; }
+  if (b_offset < 0 || b_offset + B > B_global) { set_error("bndm_white128_reinterpret_shard_f32: shard outside the global batch"); return BNDM_ERR_ARG; }
+  if (x_global == out) { set_error("bndm_white128_reinterpret_f32: in-place not supported"); return BNDM_ERR_ARG; }
+  CK(launch_white128(x_global, out, B, C, B_global, b_offset, (cudaStream_t)stream));
   return BNDM_OK;
 }
 
@@ -536,6 +674,50 @@ int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_s
     }
   delete[] owner;
   delete[] tile_of;
+  return rc;
+}
+
+// Host-only check of K1g's row schedule (CPU test-suite): every needed quad is owned by exactly one CTA slot,
+// every row group is sorted longest first (the kernel's "active quads are a prefix" rule), and the heaviest CTA's
+// load (in pipeline-stage chunks) is reported next to the total so the test can bound the imbalance.
+int bndm_debug_gemv_schedule_check(int res32, int dense, int n_ctas, int variant, int *max_load, int *total_load) {
+  if (n_ctas < 1 || variant != 0) { set_error("gemv schedule: bad argument"); return BNDM_ERR_ARG; }
+  const int kw = gemv_kw(variant);
+  int *table = new (std::nothrow) int[(size_t)n_ctas * kGemvTableStride];
+  if (!table) { set_error("out of host memory"); return BNDM_ERR_ARG; }
+  int rc = BNDM_OK;
+  const long blocks = gemv_build_schedule(res32, dense, n_ctas, variant, table);
+  if (blocks < 0) { set_error("gemv schedule: quads do not fit %d CTAs", n_ctas); rc = BNDM_ERR_UNSUPPORTED; }
+  int seen[kNPix / 4] = {0};
+  int worst = 0, total = 0;
+  for (int c = 0; c < n_ctas && rc == BNDM_OK; ++c) {
+    int load = 0;
+    if (table[c * kGemvTableStride + kGemvSlots] != total) { set_error("gemv schedule: stream offset of cta %d", c); rc = BNDM_ERR_ARG; break; }
+    for (int sl = 0; sl < kGemvSlots; ++sl) {
+      const int q = table[c * kGemvTableStride + sl];
+      if (q < 0) {           // empty slots come last (the kernel's "active slots are a prefix" rule)
+        for (int r = sl + 1; r < kGemvSlots; ++r)
+          if (table[c * kGemvTableStride + r] >= 0) { set_error("gemv schedule: hole in the slots of cta %d", c); rc = BNDM_ERR_ARG; }
+        break;
+      }
+      if (q >= kNPix / 4 || seen[q]++) { set_error("gemv schedule: quad %d out of range or owned twice", q); rc = BNDM_ERR_ARG; break; }
+      const int kend = dense ? kNPix : 4 * q + 4;
+      load += (kend + kw - 1) / kw;
+      if (sl > 0 && !dense && table[c * kGemvTableStride + sl - 1] < q) {
+        set_error("gemv schedule: slots of cta %d not sorted longest first", c); rc = BNDM_ERR_ARG; break;
+      }
+    }
+    total += load;
+    if (load > worst) worst = load;
+  }
+  if (rc == BNDM_OK && total != blocks) { set_error("gemv schedule: %d blocks counted, %ld reported", total, blocks); rc = BNDM_ERR_ARG; }
+  for (int q = 0; q < kNPix / 4 && rc == BNDM_OK; ++q) {
+    const bool needed = !res32 || (q < 512 && (q & 15) < 8);
+    if ((seen[q] != 0) != needed) { set_error("gemv schedule: quad %d %s", q, needed ? "missing" : "not needed but scheduled"); rc = BNDM_ERR_ARG; }
+  }
+  delete[] table;
+  if (max_load) *max_load = worst;
+  if (total_load) *total_load = total;
   return rc;
 }
 

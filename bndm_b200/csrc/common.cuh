@@ -80,6 +80,8 @@ struct PackArgs {
   int B, C;
   int res_mode;       // ResMode
   int src_is_image;   // BNDM_SRC_IMAGE
+  int Bg = 0;         // 128^2 image source: GLOBAL batch of the image tensor (get_noise_recent.py:131-146 mixes samples
+  int n0 = 0;         // across the batch: tile n = k*Bg + b); this call owns tiles [n0, n0 + 4 B)
 };
 cudaError_t launch_pack(const PackArgs &a, cudaStream_t s);
 
@@ -115,7 +117,7 @@ struct EpilogueArgs {
 };
 cudaError_t launch_epilogue(const EpilogueArgs &a, cudaStream_t s);
 
-cudaError_t launch_white128(const float *x, float *out, int B, int C, cudaStream_t s);
+cudaError_t launch_white128(const float *x, float *out, int B, int C, int Bg, int b0, cudaStream_t s);
 // L -> stage blocks [Lh tile | Ll tile] in the SWIZZLE_128B shared-memory image (noise_gemm_tc.cu);
 // n_blocks = 2112 (lower-triangular, blocks of row tile i start at 2 i (i + 1)) or 4096 (dense)
 cudaError_t launch_tile_L(const float *L, float *Lt, int dense, int raw, cudaStream_t s);
@@ -202,6 +204,32 @@ bool tc_fused_combine(int nb);
 bool tc_raw_L(int nb, int n_colblk);   // policy: raw-L converter variant for this shape?
 int tc_sub(int nb, bool raw);          // policy: k-stages per pipeline stage (2 = 32 KiB L requests)
 void tc_set_policy(int fused, int raw);   // policy: combine fused into the contraction for this column block?
+
+// ---- K1g: streaming fp32 contraction for <= kGemvMaxCols columns (noise_gemv.cu) -------------
+constexpr int kGemvSlots = 8;      // quads (4 consecutive rows of L) a CTA may own
+constexpr int kGemvMaxCols = 16;
+constexpr int kGemvAutoCols = 12;  // the default rule picks K1g up to here (the 16-column instance spills: K1b is as fast there)
+constexpr int kGemvTraceStride = 128;   // u64 per CTA of K1g's debug trace: [0..3] summary, [8+c] stage c requested, [48+c] landed, [88+c] released
+constexpr int kGemvTableStride = 10;   // ints per CTA in the schedule table: 8 slots, first stream block, load
+struct GemvArgs {
+  const float *Lg;         // L in K1g's stream order (launch_gemv_pack_L)
+  const float *z_cols;     // white columns [n_cols][4096]
+  const int *sched;        // device, [n_ctas][kGemvTableStride] (gemv_build_schedule)
+  int n_ctas;
+  int dense;               // L is not lower-triangular (or the caller forces the dense walk)
+  int variant;             // gemv_variant()
+  const float *gamma;      // [B] or null
+  float *out, *out_bn, *out_wn;
+  int n_cols, B, C, res_mode;
+  TrainOut train;
+  unsigned long long *trace;
+};
+cudaError_t launch_gemv(const GemvArgs &a, cudaStream_t s);
+long gemv_build_schedule(int res32, int dense, int n_ctas, int variant, int *table);   // -> blocks of 4 x KW floats, -1: no fit
+cudaError_t launch_gemv_pack_L(const float *L, float *Lg, const int *table_dev, int n_ctas, int variant, int dense, cudaStream_t s);
+int gemv_kw(int variant);
+int gemv_variant();
+bool gemv_policy();                 // BNDM_GEMV=0 turns the automatic choice of K1g off (A/B measurements)
 
 // combine of the stream-K partials + everything get_noise_v2 does after the matmul
 struct CombineArgs {

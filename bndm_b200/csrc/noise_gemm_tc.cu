@@ -47,78 +47,13 @@
 
 #include "common.cuh"
 #include "out_map.cuh"
+#include "ptx.cuh"
 
 namespace bndm {
 
 constexpr int kUmmaK = 8;                         // tf32: 32 bytes of K per tcgen05.mma
 constexpr int kThreads = 192;
 constexpr int kThreadsRaw = 320;                  // + 4 converter warps
-constexpr uint32_t kSpinLimit = 1u << 27;         // bounded spins: a protocol bug traps instead of hanging the GPU
-
-// L2 eviction-priority policies for bulk loads (createpolicy encodings)
-constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
-constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
-
-// ---------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > kSpinLimit) __trap();
-  }
-}
-// one lane of a converged warp (warp-uniform control flow around it keeps descriptors and
-// addresses in uniform registers: no per-instruction R2UR traffic in the issue loops)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-
-// linear global -> shared bulk copy (TMA engine), completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
-      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-
-// 2-D tiled TMA load (tensor map), 128-byte swizzle applied by the hardware, OOB rows zero-filled
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
-
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
   asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -187,11 +122,6 @@ struct TcKernelArgs {
   int n_cols;
 };
 
-__device__ __forceinline__ unsigned long long gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 // One (<= chain)-stage piece of a segment; every role walks the same sequence.
 struct ChainWalk {
@@ -257,7 +187,7 @@ gemm_tc_kernel(const TcKernelArgs a, const __grid_constant__ CUtensorMap map_z) 
   static_assert(NB % 16 == 0 && NB >= 16 && NB <= 128, "column block must be a multiple of 16 in [16, 128]");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t *base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // keeps the shared address space (LDS/STS, not generic)
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(base + (size_t)a.stages * kStageBytes);
   uint64_t *empty_bar = full_bar + a.stages;
   uint64_t *acc_full = empty_bar + a.stages;      // [2]
@@ -640,11 +570,7 @@ static int tc_chain() {
   return v;
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
+EncodeTiledFn get_tensormap_encoder() {
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
   void *p = nullptr;
@@ -657,7 +583,7 @@ static EncodeTiledFn get_encode() {
 
 // fp32 columns [rows][4096] row-major, box = [box_rows][32 k], 128-byte swizzle, OOB rows read as zero
 static bool make_z_map(CUtensorMap *m, const float *ptr, int rows, int box_rows) {
-  EncodeTiledFn enc = get_encode();
+  EncodeTiledFn enc = get_tensormap_encoder();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)kNPix, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)kNPix * 4};

@@ -29,8 +29,10 @@ __global__ void __launch_bounds__(256) pack_kernel(PackArgs a) {
     } else if (a.res_mode == kRes32) {          // 2x2 periodic tiling of a 32x32 image (:78-79)
       v = ld4(a.src + (int64_t)j * 1024 + (h & 31) * 32 + (w & 31));
     } else {                                    // quadrant k of image b (:131-132)
-      const int n = j / a.C, c = j - n * a.C;
-      const int k = n / a.B, b = n - k * a.B;
+      // tile n of the GLOBAL dim-0 concatenation (a shard owns tiles [n0, n0 + 4 B) of the 4 Bg)
+      const int nl = j / a.C, c = j - nl * a.C;
+      const int n = nl + a.n0;
+      const int k = n / a.Bg, b = n - k * a.Bg;
       const int r0 = (k >> 1) * kTile, c0 = (k & 1) * kTile;
       v = ld4(a.src + (((int64_t)b * a.C + c) * 128 + r0 + h) * 128 + c0 + w);
     }
@@ -59,10 +61,11 @@ cudaError_t launch_pack(const PackArgs &a, cudaStream_t s) {
 
 // ---- 'gaussian' 128^2 test-mode pass-through (get_noise_recent.py:50-56) ------------------
 // out[b', c', r0+h, c0+w] = x_tile[n][f % C][f / C],  n = 4 b' + k', f = c'*4096 + h*64 + w,
-// x_tile[n = k*B + b] = quadrant k of image b; placement (r0,c0) = ((k'&1)*64, (k'>>1)*64).
+// x_tile[n = k*Bg + b] = quadrant k of image b of the GLOBAL batch Bg (the shard [b0, b0+B) computes its own
+// output images only); placement (r0,c0) = ((k'&1)*64, (k'>>1)*64).
 __global__ void __launch_bounds__(256) white128_kernel(const float *__restrict__ x, float *__restrict__ out,
-                                                       int B, int C) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*C*128*128
+                                                       int B, int C, int Bg, int b0) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over B*C*128*128 (this shard's outputs)
   const int64_t total = (int64_t)B * C * 128 * 128;
   if (idx >= total) return;
   const int X = (int)(idx & 127), Y = (int)((idx >> 7) & 127);
@@ -70,17 +73,17 @@ __global__ void __launch_bounds__(256) white128_kernel(const float *__restrict__
   const int bo = bc / C, co = bc - bo * C;
   const int kq = ((X >> 6) << 1) | (Y >> 6);          // inverse of the output placement
   const int h = Y & 63, w = X & 63;
-  const int n = bo * 4 + kq;
+  const int n = (bo + b0) * 4 + kq;                   // tile index in the GLOBAL (4 Bg, ...) concatenation
   const int f = co * kNPix + h * kTile + w;
   const int c = f % C, p = f / C;
-  const int k = n / B, b = n - k * B;
+  const int k = n / Bg, b = n - k * Bg;
   const int r0 = (k >> 1) * kTile, c0 = (k & 1) * kTile;
   out[idx] = x[(((int64_t)b * C + c) * 128 + r0 + (p >> 6)) * 128 + c0 + (p & 63)];
 }
 
-cudaError_t launch_white128(const float *x, float *out, int B, int C, cudaStream_t s) {
+cudaError_t launch_white128(const float *x, float *out, int B, int C, int Bg, int b0, cudaStream_t s) {
   const int64_t total = (int64_t)B * C * 128 * 128;
-  white128_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, out, B, C);
+  white128_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x, out, B, C, Bg, b0);
   return cudaGetLastError();
 }
 

@@ -17,7 +17,7 @@ import torch
 from . import _lib
 
 BLUE_TYPES = ("gaussianBN", "gaussianRN", "GBN")
-_GEMM_FLAGS = {"tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT}
+_GEMM_FLAGS = {"auto": _lib.GEMM_AUTO, "tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT, "gemv": _lib.GEMM_GEMV}
 
 
 class CovMatL:
@@ -87,35 +87,48 @@ def prepare_L(cov_mat_L, max_columns: int = 192) -> CovMatL:
     return h
 
 
-def _white128_reinterpret(x):
-    out = torch.empty_like(x)
+def _white128_reinterpret(x, lo=0, count=None):
+    count = x.shape[0] if count is None else count
+    out = torch.empty((count,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device):
-        rc = _lib.load().bndm_white128_reinterpret_f32(_lib.ptr(x), _lib.ptr(out), x.shape[0], x.shape[1],
-                                                       _lib.current_stream(x.device))
-    _lib.check(rc, "bndm_white128_reinterpret_f32")
+        rc = _lib.load().bndm_white128_reinterpret_shard_f32(_lib.ptr(x), _lib.ptr(out), count, x.shape[1], x.shape[0], lo,
+                                                             _lib.current_stream(x.device))
+    _lib.check(rc, "bndm_white128_reinterpret_shard_f32")
     return out
 
 
 def get_noise_v2(device, x, cov_mat_L, alpha_t, time_step=None, noise_type="gaussian", train_or_test="train",
-                 inplace=False, *, gemm="tc", want=("noise", "bn", "wn")):
+                 inplace=False, *, gemm="auto", want=("noise", "bn", "wn"), shard=None):
     """Drop-in for bluenoise/get_noise_recent.py:23.
 
     ``alpha_t`` is the per-sample WHITE fraction gamma (B,) -- out = bn*(1-gamma) + wn*gamma
     (:91,:116,:160).  ``time_step`` is unused, as in the reference.  Extra keyword-only
-    arguments: ``gemm`` in {'tc' (tcgen05 3xTF32), 'simt' (fp32 FFMA)}; ``want`` lets callers
-    that ignore noise_bn / noise_wn skip writing them (those entries are returned as None).
+    arguments: ``gemm`` in {'auto' (K1g streaming fp32 kernel for <= 16 columns, tcgen05 above), 'tc' (tcgen05
+    3xTF32), 'gemv' (K1g), 'simt' (fp32 FFMA split-K witness)}; ``want`` lets callers
+    that ignore noise_bn / noise_wn skip writing them (those entries are returned as None);
+    ``shard=(lo, hi)``: ``x`` (and ``alpha_t``, if it has one entry per global sample) describe the WHOLE batch
+    of a run that is split across GPUs and the call returns samples ``[lo, hi)`` only, bit-identical to
+    the same rows of the unsharded call -- including the 128^2 ``inplace=True`` branch, which mixes
+    samples across the batch (:131-146), and the draw, which is made for the global shape so that
+    identical seeds give identical fields on any number of GPUs.
     """
     if x.dim() != 4:
         raise ValueError("x must be (B, C, H, W)")
     res = x.shape[-1]
-    bs, dimension = x.shape[0], x.shape[1]
+    bs_g, dimension = x.shape[0], x.shape[1]
+    lo, hi = (0, bs_g) if shard is None else (int(shard[0]), int(shard[1]))
+    if not (0 <= lo < hi <= bs_g):
+        raise ValueError(f"shard {shard} outside the batch of {bs_g}")
+    bs = hi - lo
 
     if noise_type == "gaussian":                                   # :31-67, pass-through
         if res not in (64, 128):
             raise NotImplementedError
         noise = x if inplace else torch.randn_like(x)
         if res == 128 and train_or_test == "test":                 # :50-56 (built from x, not the draw)
-            noise = _white128_reinterpret(_lib.require_cuda_f32(x, "x"))
+            noise = _white128_reinterpret(_lib.require_cuda_f32(x, "x"), lo, bs)
+        elif shard is not None:
+            noise = noise[lo:hi]
         return noise, noise, noise
 
     if noise_type == "uniform":
@@ -133,7 +146,7 @@ def get_noise_v2(device, x, cov_mat_L, alpha_t, time_step=None, noise_type="gaus
     if L.device != x.device:
         raise ValueError(f"cov_mat_L is on {L.device}, x on {x.device}")
 
-    # ---- the white field: drawn where and how the reference draws it
+    # ---- the white field: drawn where and how the reference draws it (for the GLOBAL batch)
     if inplace:
         z, src = x, _lib.SRC_IMAGE
     else:
@@ -141,14 +154,16 @@ def get_noise_v2(device, x, cov_mat_L, alpha_t, time_step=None, noise_type="gaus
         if res == 64:
             z = torch.randn_like(x)                                                    # :108
         elif res == 32:
-            z = torch.randn(bs, dimension, 64, 64, dtype=x.dtype, device=x.device)     # :78-83 randn_like(tiled x)
+            z = torch.randn(bs_g, dimension, 64, 64, dtype=x.dtype, device=x.device)   # :78-83 randn_like(tiled x)
         else:
-            z = torch.randn(bs * 4, dimension, 64, 64).float().to(device)              # :138 (CPU generator)
+            z = torch.randn(bs_g * 4, dimension, 64, 64).float().to(device)            # :138 (CPU generator)
             z = _lib.require_cuda_f32(z, "white draw")
 
     gamma = None
     if noise_type in ("gaussianBN", "gaussianRN"):
         gamma = _lib.require_cuda_f32(alpha_t.reshape(-1), "alpha_t")
+        if shard is not None and gamma.numel() == bs_g:
+            gamma = gamma[lo:hi].contiguous()
         if gamma.numel() != bs:
             raise ValueError(f"alpha_t must have {bs} entries, got {gamma.numel()}")
 
@@ -157,9 +172,9 @@ def get_noise_v2(device, x, cov_mat_L, alpha_t, time_step=None, noise_type="gaus
     out_bn = torch.empty_like(out) if (gamma is not None and "bn" in want) else None
     out_wn = torch.empty_like(out) if "wn" in want else None
     with torch.cuda.device(x.device):
-        rc = _lib.load().bndm_get_noise_f32(L._h, _lib.ptr(z), _lib.ptr(gamma), _lib.ptr(out), _lib.ptr(out_bn),
-                                            _lib.ptr(out_wn), bs, dimension, res, src | _GEMM_FLAGS[gemm],
-                                            _lib.current_stream(x.device))
+        rc = _lib.load().bndm_get_noise_shard_f32(L._h, _lib.ptr(z), _lib.ptr(gamma), _lib.ptr(out), _lib.ptr(out_bn),
+                                                  _lib.ptr(out_wn), bs, dimension, res, src | _GEMM_FLAGS[gemm], bs_g, lo,
+                                                  _lib.current_stream(x.device))
     _lib.check(rc, "bndm_get_noise_f32")
     if gamma is None:          # 'GBN': noise IS noise_bn (:118)
         out_bn = out
@@ -170,7 +185,7 @@ get_noise = get_noise_v2   # the name BASELINE.json's north_star uses
 
 
 def get_noise_train(device, x1, cov_mat_L, gamma_t, alpha, alpha_prev=None, noise_type="gaussianBN", *, draw=None,
-                    want_x0=False, gemm="tc"):
+                    want_x0=False, gemm="auto"):
     """The noise + blend front end of one IADB training step (iadb_bn.py:881-954) in one call:
 
         x0, bn, wn = get_noise_v2(device, x1, L, gamma_t, t, noise_type, 'train', inplace=False)

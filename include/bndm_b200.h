@@ -46,9 +46,13 @@ enum {
                                  res 32 is tiled 2x2 (:78-79), res 128 is cut in quadrants
                                  concatenated on dim 0 (:131-132)                              */
 /* Which contraction kernel:                                                                 */
-#define BNDM_GEMM_TC      0u  /* tcgen05 / TMA, error-compensated 3xTF32 (default)            */
-#define BNDM_GEMM_SIMT    16u /* fp32 FFMA reference kernel (same results to ~1e-6)           */
+#define BNDM_GEMM_AUTO    0u  /* default: K1g for <= 12 GEMM columns (HBM-bound GEMV regime),
+                                 K1b (tcgen05) above                                          */
+#define BNDM_GEMM_SIMT    16u /* fp32 FFMA split-K witness kernel (same results to ~1e-6)     */
 #define BNDM_FORCE_DENSE  32u /* ignore the triangular structure of L (testing)               */
+#define BNDM_GEMM_GEMV    64u /* force K1g: TMA-streamed fp32 FFMA kernel, complete rows per
+                                 CTA, one launch, no split-K (<= 16 columns, else UNSUPPORTED) */
+#define BNDM_GEMM_TC      128u /* force K1b: tcgen05 / TMA, error-compensated 3xTF32, stream-K */
 
 typedef struct bndm_L bndm_L; /* opaque: L + its tcgen05 operand copies + workspace           */
 
@@ -92,6 +96,16 @@ int bndm_profile_last_ms(bndm_L *h, float *pack_ms, float *gemm_ms, float *epilo
 int bndm_get_noise_f32(bndm_L *h, const float *z, const float *gamma, float *out, float *out_bn,
                        float *out_wn, int B, int C, int res, unsigned flags, void *stream);
 
+/* The same call for ONE SHARD of a batch that is split across GPUs: `z_global` is the white field of
+ * the WHOLE batch (B_global samples; layout per BNDM_SRC_* with B = B_global), the outputs and gamma cover samples
+ * [b_offset, b_offset + B) only.  Needed because the 128^2 `inplace=True` branch mixes samples across the batch
+ * (get_noise_recent.py:131-146: tile n = k*B_global + b is re-read as (b', k') = divmod(n, 4)), so a shard's outputs
+ * depend on other shards' white quadrants; for every other branch this equals the unsharded call on the slice.
+ * Results are bit-identical to rows [b_offset, b_offset + B) of the unsharded call.                              */
+int bndm_get_noise_shard_f32(bndm_L *h, const float *z_global, const float *gamma, float *out, float *out_bn,
+                             float *out_wn, int B, int C, int res, unsigned flags, int B_global, int b_offset,
+                             void *stream);
+
 /* Training-side fusion (iadb_bn.py:881-954, latent_iadb_bn_diffusers.py:606-633): the
  * same contraction, with the epilogue emitting what the training step builds from get_noise_v2's
  * three results instead of (or next to) them:
@@ -109,6 +123,9 @@ int bndm_get_noise_train_f32(bndm_L *h, const float *z, const float *gamma, cons
 /* 'gaussian' pass-through at 128^2 with train_or_test=='test' (get_noise_recent.py:50-56):
  * out = noise_padding(reinterpret(quadrants(x))).  x, out: (B,C,128,128), no aliasing.     */
 int bndm_white128_reinterpret_f32(const float *x, float *out, int B, int C, void *stream);
+/* Same for one shard: x_global is (B_global,C,128,128), out covers samples [b_offset, b_offset + B).           */
+int bndm_white128_reinterpret_shard_f32(const float *x_global, float *out, int B, int C, int B_global, int b_offset,
+                                        void *stream);
 
 /* IADB update (iadb_bn.py:326,329,344; utils.py:218,221,226; latent...:110,113,117):
  *     x_out = (x + dalpha[b]*d[:, :C]) + dgamma[b]*d[:, C:2C]      (d_channels == 2C)
@@ -156,7 +173,9 @@ int bndm_debug_set_policy(int fused_combine, int raw_L);
 
 /* Debug: when `trace_dev` (device, 24 x u64 per CTA, >= 148 CTAs) is non-NULL the tcgen05
  * contraction kernel records per-CTA time stamps {globaltimer in, clock in, after init, first
- * operands landed, last MMA issued, epilogue done, clock out, globaltimer out}.               */
+ * operands landed, last MMA issued, epilogue done, clock out, globaltimer out}.  K1g uses 128 x u64 per CTA:
+ * [0] start, [1] first stage landed, [2] stream consumed, [3] outputs stored, [8+c] stage c requested, [48+c] stage c
+ * landed (seen by the warp of the longest quad), [88+c] released by it (%globaltimer, c < 40).                    */
 int bndm_debug_set_trace(bndm_L *h, unsigned long long *trace_dev);
 
 /* Host-only consistency check of the contraction kernel's stream-K work split (no device
@@ -166,6 +185,11 @@ int bndm_debug_streamk_check(int n_tiles, int dense, int n_colblk, int num_sms);
 /* Same with `sub` k-stages per schedule unit (1, or 2 = the 64-k pipeline stages of the raw-operand
  * variant).                                                                                    */
 int bndm_debug_streamk_check_sub(int n_tiles, int dense, int n_colblk, int num_sms, int sub);
+
+/* Host-only check of K1g's row schedule (no device work; CPU test-suite): 0 if every quad of 4 rows the branch needs
+ * (all 1024, or the 256 with h,w < 32 at 32^2) is owned by exactly one CTA and every row group is sorted longest
+ * first; *max_load / *total_load = heaviest CTA's / all CTAs' pipeline-stage chunks (load balance).  variant: 0.      */
+int bndm_debug_gemv_schedule_check(int res32, int dense, int n_ctas, int variant, int *max_load, int *total_load);
 
 /* K5 -- the UNet's normalisation glue on channels-last activations (diffusers ResnetBlock2D
  * norm/act sequence of the model built at iadb_bn.py:205-282 and called at :319), one kernel:

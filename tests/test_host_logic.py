@@ -204,6 +204,27 @@ def test_streamk_schedule_is_consistent():
                     assert rc == 0, (n_tiles, dense, n_colblk, sms, "sub=2", lib.bndm_last_error())
 
 
+def test_gemv_row_schedule_covers_every_quad_once_and_is_balanced():
+    """K1g's row ownership (csrc/noise_gemv.cu): every needed quad of 4 rows belongs to exactly one CTA slot, row groups
+    are sorted longest first, and no CTA streams more than 2.5 % above the mean at the full triangular size."""
+    import ctypes as C
+    from bndm_b200 import _lib
+    lib = _lib.load()
+    for variant in (0,):
+        for res32 in (0, 1):
+            for dense in (0, 1):
+                for sms in (148, 132, 160):
+                    worst, total = C.c_int(), C.c_int()
+                    rc = lib.bndm_debug_gemv_schedule_check(res32, dense, sms, variant, C.byref(worst), C.byref(total))
+                    assert rc == 0, (variant, res32, dense, sms, lib.bndm_last_error())
+                    # longest-first dealing: never more than one longest quad above the mean ...
+                    assert worst.value <= total.value / sms + 32, (variant, dense, sms, worst.value)
+                    if not res32 and not dense and sms == 148:       # ... and within 2.5 % at the production shape
+                        assert worst.value <= 1.025 * total.value / sms, (variant, worst.value, total.value)
+    # 1024 quads do not fit 100 CTAs x 8 slots: reported, not silently truncated
+    assert lib.bndm_debug_gemv_schedule_check(0, 0, 100, 0, None, None) == _lib.ERR_UNSUPPORTED
+
+
 def test_fused_unet_and_training_front_end_refuse_cpu():
     """No CPU fallback anywhere in the product: the fused evaluator and the training-side entry raise."""
     import bndm_b200 as bb

@@ -11,7 +11,18 @@ from oracle import noise as on
 
 pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda:0")
-GEMMS = ["tc", "simt"]
+GEMMS = ["tc", "simt", "gemv"]
+FLAG = {"auto": _lib.GEMM_AUTO, "tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT, "gemv": _lib.GEMM_GEMV}
+
+
+def _skip_wide_gemv(gemm, n_cols):
+    """K1g covers the GEMV regime only (<= 16 GEMM columns); wider calls are K1b's."""
+    if gemm == "gemv" and n_cols > 16:
+        pytest.skip("K1g handles <= 16 columns")
+
+
+def _cols(res, bs, C):
+    return bs * C * (4 if res == 128 else 1)
 
 
 @pytest.fixture(scope="module")
@@ -37,6 +48,8 @@ def test_native_library_is_loaded():
 def test_golden(name, gemm, L_dev):
     g = load_golden(name)
     nt, inplace, tt = str(g["noise_type"]), bool(g["inplace"]), str(g["train_or_test"])
+    if nt != "gaussian":
+        _skip_wide_gemv(gemm, _cols(g["x"].shape[-1], g["x"].shape[0], g["x"].shape[1]))
     x = torch.from_numpy(g["x"].copy()).to(DEV)
     gamma = torch.from_numpy(g["gamma"]).to(DEV)
     if inplace or nt == "gaussian":
@@ -57,20 +70,27 @@ def _call_with_draw(L_dev, draw, gamma, shape, noise_type, gemm):
     wn = torch.empty(shape, device=DEV)
     g = None if noise_type == "GBN" else gamma
     rc = _lib.load().bndm_get_noise_f32(h._h, _lib.ptr(draw), _lib.ptr(g), _lib.ptr(out), _lib.ptr(bn), _lib.ptr(wn),
-                                        bs, C, res, _lib.SRC_DRAW | {"tc": 0, "simt": 16}[gemm],
+                                        bs, C, res, _lib.SRC_DRAW | FLAG[gemm],
                                         _lib.current_stream(DEV))
     _lib.check(rc, "bndm_get_noise_f32")
     return out, bn, wn
 
 
+# BASELINE shard shapes: cfg 1 (64, 4, 3); cfg 2 (64, 64, 3) = 2 x 96 columns; cfg 4 per GPU (128, 32, 3) = 384 columns
+# = 3 x 128 through the 128^2 output map; cfg 5 per GPU (64, 16, 4) = 64 columns.  (32, 64, 4) and (32, 50, 3) /
+# (128, 16, 3) and (128, 9, 4) are the multi-column-block cases of the 32^2 / 128^2 branches.
 CASES = [(64, 4, 3), (64, 1, 1), (64, 7, 4), (64, 64, 3), (32, 3, 4), (32, 1, 1), (128, 2, 3), (128, 1, 4),
-         (128, 5, 3), (64, 100, 3)]
+         (128, 5, 3), (64, 100, 3), (128, 32, 3), (64, 16, 4), (32, 64, 4), (32, 50, 3), (128, 16, 3), (128, 9, 4),
+         (64, 5, 3), (64, 4, 4), (128, 1, 3)]
 
 
 @pytest.mark.parametrize("gemm", GEMMS)
 @pytest.mark.parametrize("noise_type", ["gaussianBN", "GBN"])
 @pytest.mark.parametrize("res,bs,C", CASES)
 def test_vs_oracle_inplace(res, bs, C, noise_type, gemm, L_np, L_dev):
+    _skip_wide_gemv(gemm, _cols(res, bs, C))
+    if gemm == "simt" and _cols(res, bs, C) > 300:
+        pytest.skip("the fp32 witness kernel is covered at smaller sizes")
     rng = np.random.default_rng(res + 7 * bs + C)
     x = rng.standard_normal((bs, C, res, res)).astype(np.float32)
     gamma = rng.random(bs).astype(np.float32)
@@ -88,7 +108,7 @@ def test_vs_oracle_inplace(res, bs, C, noise_type, gemm, L_np, L_dev):
         assert got[0] is got[1]                      # get_noise_recent.py:118: noise = noise_bn
 
 
-@pytest.mark.parametrize("res,bs,C", [(64, 3, 3), (32, 2, 4), (128, 2, 3)])
+@pytest.mark.parametrize("res,bs,C", [(64, 3, 3), (32, 2, 4), (128, 2, 3), (128, 32, 3), (32, 64, 4), (64, 16, 4), (128, 1, 3)])
 def test_draw_path_uses_torch_rng_like_reference(res, bs, C, L_np, L_dev):
     x = torch.zeros(bs, C, res, res, device=DEV)
     gamma = torch.rand(bs, device=DEV)
@@ -135,8 +155,8 @@ def test_errors_mirror_reference(L_dev):
 # ------------------------------------------------------------------ properties (any size)
 @pytest.mark.parametrize("gemm", GEMMS)
 def test_gamma_one_is_white_and_gamma_zero_is_blue(gemm, L_dev):
-    x = torch.randn(6, 3, 64, 64, device=DEV)
-    one = torch.ones(6, device=DEV)
+    x = torch.randn(5, 3, 64, 64, device=DEV)
+    one = torch.ones(5, device=DEV)
     out, bn, wn = bb.get_noise_v2(DEV, x, L_dev, one, None, "gaussianBN", "train", True, gemm=gemm)
     assert torch.equal(wn, x)
     assert torch.equal(out, bn * 0.0 + x)           # bn*(1-1) + wn*1, exactly
@@ -172,7 +192,7 @@ def test_triangular_skip_equals_dense(gemm, L_np, L_dev):
     for extra in (0, _lib.FORCE_DENSE):
         o = torch.empty_like(x)
         rc = _lib.load().bndm_get_noise_f32(h._h, _lib.ptr(x), None, _lib.ptr(o), None, None, 3, 3, 64,
-                                            _lib.SRC_IMAGE | {"tc": 0, "simt": 16}[gemm] | extra,
+                                            _lib.SRC_IMAGE | FLAG[gemm] | extra,
                                             _lib.current_stream(DEV))
         _lib.check(rc, "get_noise")
         outs.append(o)
@@ -185,6 +205,24 @@ def test_triangular_skip_equals_dense(gemm, L_np, L_dev):
     got = bb.get_noise_v2(DEV, x, hd, None, None, "GBN", "train", True, gemm=gemm)[1]
     want = on.get_noise_np(_np(x), Ld, None, "GBN", "train", True)[1]
     np.testing.assert_allclose(_np(got), want, rtol=RTOL, atol=ATOL)
+
+
+def test_gemv_matches_tc_and_simt_closely(L_dev):
+    x = torch.randn(4, 3, 64, 64, device=DEV)
+    g = torch.rand(4, device=DEV)
+    r = {k: bb.get_noise_v2(DEV, x, L_dev, g, None, "gaussianBN", "train", True, gemm=k)[0] for k in ("gemv", "tc", "simt", "auto")}
+    assert torch.equal(r["auto"], r["gemv"]), "12 columns: the default rule picks K1g"
+    assert (r["gemv"] - r["simt"]).abs().max().item() < 4e-6
+    assert (r["gemv"] - r["tc"]).abs().max().item() < 4e-6
+
+
+def test_forced_kernel_flags(L_dev):
+    x = torch.randn(8, 3, 64, 64, device=DEV)                      # 24 columns: beyond K1g
+    with pytest.raises(NotImplementedError):
+        bb.get_noise_v2(DEV, x, L_dev, None, None, "GBN", "train", True, gemm="gemv")
+    a = bb.get_noise_v2(DEV, x, L_dev, None, None, "GBN", "train", True, gemm="auto")[0]
+    b = bb.get_noise_v2(DEV, x, L_dev, None, None, "GBN", "train", True, gemm="tc")[0]
+    assert torch.equal(a, b), "24 columns: the default rule picks K1b"
 
 
 def test_tc_matches_simt_closely(L_dev):
@@ -238,6 +276,84 @@ def policy():
     lib.bndm_debug_set_policy(-1, -1)
 
 
+@pytest.mark.parametrize("res,bs,C,noise_type,inplace", [(64, 4, 3, "gaussianBN", True), (64, 4, 4, "gaussianBN", True),
+                                                         (64, 1, 3, "GBN", True), (32, 3, 4, "gaussianBN", True),
+                                                         (32, 4, 4, "gaussianBN", False), (128, 1, 3, "gaussianBN", True),
+                                                         (128, 1, 4, "gaussianBN", False), (64, 2, 4, "gaussianRN", False)])
+def test_gemv_instances_match_oracle(res, bs, C, noise_type, inplace, L_np, L_dev):
+    """K1g at every column-count instantiation (4, 8, 12, 16), every branch, through the C ABI with its own handle;
+    run-to-run bit-identical."""
+    h = bb.CovMatL(L_dev)
+    rng = np.random.default_rng(77 + res + bs + C)
+    x = rng.standard_normal((bs, C, res, res)).astype(np.float32)
+    gamma = rng.random(bs).astype(np.float32)
+    draw = None if inplace else rng.standard_normal((bs * (4 if res == 128 else 1), C, 64, 64)).astype(np.float32)
+    want = on.get_noise_np(x, L_np, gamma, noise_type, "train", inplace, draw)
+    shape = (bs, C, res, res)
+    outs = []
+    for _ in range(2):
+        o = [torch.empty(shape, device=DEV) for _ in range(3)]
+        src = torch.from_numpy(x if inplace else draw).to(DEV)
+        g = None if noise_type == "GBN" else torch.from_numpy(gamma).to(DEV)
+        rc = _lib.load().bndm_get_noise_f32(h._h, _lib.ptr(src), _lib.ptr(g), _lib.ptr(o[0]), _lib.ptr(o[1]), _lib.ptr(o[2]),
+                                            bs, C, res, (_lib.SRC_IMAGE if inplace else _lib.SRC_DRAW) | _lib.GEMM_GEMV,
+                                            _lib.current_stream(DEV))
+        _lib.check(rc, "bndm_get_noise_f32")
+        outs.append(o)
+    for a_, b_, w_, nm in zip(outs[0], outs[1], want, ("noise", "bn", "wn")):
+        assert torch.equal(a_, b_), nm
+        if nm == "wn":
+            assert np.array_equal(_np(a_), w_)
+        else:
+            np.testing.assert_allclose(_np(a_), w_, rtol=RTOL, atol=ATOL, err_msg=nm)
+    h.close()
+
+
+@pytest.mark.parametrize("res,bs,C,inplace", [(128, 8, 3, True), (128, 6, 3, False), (64, 8, 3, True), (32, 8, 4, True),
+                                              (32, 6, 4, False), (128, 3, 4, True)])
+def test_sharded_call_equals_rows_of_the_unsharded_call(res, bs, C, inplace, L_dev):
+    """SURVEY 8e seed-parity rule incl. the 128^2 inplace branch, whose (b', k') = divmod(k*bs + b, 4) mixing uses the
+    GLOBAL batch (get_noise_recent.py:131-146): every shard of the global field reproduces the same rows of the full
+    call -- the white field bit for bit; the blue field to a few ulp (the contraction's instance and split-K cut
+    depend on the column count, so different shard sizes add the same products in another order), and bit for bit
+    whenever the shard runs the same kernel instance (same shard size, or the batch-invariant K1g)."""
+    x = torch.randn(bs, C, res, res, device=DEV)
+    gamma = torch.rand(bs, device=DEV)
+    torch.manual_seed(5)
+    full = bb.get_noise_v2(DEV, x, L_dev, gamma, None, "gaussianBN", "test", inplace)
+    parts = {}
+    for lo, hi in ((0, bs // 2), (bs // 2, bs), (1, 2), (0, bs)):
+        torch.manual_seed(5)
+        part = parts[(lo, hi)] = bb.get_noise_v2(DEV, x, L_dev, gamma, None, "gaussianBN", "test", inplace, shard=(lo, hi))
+        for f_, p_, nm in zip(full, part, ("noise", "bn", "wn")):
+            assert p_.shape[0] == hi - lo
+            if nm == "wn" or (lo, hi) == (0, bs):
+                assert torch.equal(p_, f_[lo:hi]), (nm, lo, hi)
+            else:
+                np.testing.assert_allclose(_np(p_), _np(f_[lo:hi]), rtol=1e-5, atol=2e-6, err_msg=f"{nm} {lo}:{hi}")
+    # the same global field cut at the same size on "another rank": bit-identical (this is what N-GPU == 1-GPU means)
+    torch.manual_seed(5)
+    again = bb.get_noise_v2(DEV, x.clone(), L_dev, gamma.clone(), None, "gaussianBN", "test", inplace, shard=(0, bs // 2))
+    for a_, p_ in zip(again, parts[(0, bs // 2)]):
+        assert torch.equal(a_, p_)
+    if res == 128:          # the 'gaussian' test-mode pass-through has the same mixing (:50-56)
+        fullg = bb.get_noise_v2(DEV, x, L_dev, None, None, "gaussian", "test", True)[0]
+        partg = bb.get_noise_v2(DEV, x, L_dev, None, None, "gaussian", "test", True, shard=(1, bs - 1))[0]
+        assert torch.equal(partg, fullg[1:bs - 1])
+
+
+def test_gemv_is_batch_invariant(L_dev):
+    """K1g adds a column's products in an order that does not depend on the other columns: a sample's result is the
+    same bits whether it is computed alone or in a batch of 4."""
+    x = torch.randn(4, 3, 64, 64, device=DEV)
+    g = torch.rand(4, device=DEV)
+    full = bb.get_noise_v2(DEV, x, L_dev, g, None, "gaussianBN", "train", True, gemm="gemv")
+    for b in range(4):
+        one = bb.get_noise_v2(DEV, x, L_dev, g, None, "gaussianBN", "train", True, gemm="gemv", shard=(b, b + 1))
+        for f_, o_ in zip(full, one):
+            assert torch.equal(o_, f_[b:b + 1])
+
+
 @pytest.mark.parametrize("fused", [0, 1])
 @pytest.mark.parametrize("raw", [0, 1])
 @pytest.mark.parametrize("res,bs,C", [(64, 4, 3), (64, 20, 3), (64, 40, 3), (32, 5, 4), (128, 3, 3), (64, 50, 3)])
@@ -250,8 +366,8 @@ def test_contraction_variants_match_oracle(res, bs, C, fused, raw, policy, L_np,
     gamma = rng.random(bs).astype(np.float32)
     want = on.get_noise_np(x, L_np, gamma, "gaussianBN", "train", True)
     xt, gt = torch.from_numpy(x).to(DEV), torch.from_numpy(gamma).to(DEV)
-    got = bb.get_noise_v2(DEV, xt, L_dev, gt, None, "gaussianBN", "train", True)
-    again = bb.get_noise_v2(DEV, xt, L_dev, gt, None, "gaussianBN", "train", True)
+    got = bb.get_noise_v2(DEV, xt, L_dev, gt, None, "gaussianBN", "train", True, gemm="tc")
+    again = bb.get_noise_v2(DEV, xt, L_dev, gt, None, "gaussianBN", "train", True, gemm="tc")
     for g_, a_, w_, nm in zip(got, again, want, ("noise", "bn", "wn")):
         assert torch.equal(g_, a_), nm
         if nm == "wn":
@@ -269,16 +385,23 @@ def test_unit_variance_blue_L_accuracy(bs):
     x = torch.randn(bs, 3, 64, 64, device=DEV)
     ref = (x.double().reshape(bs * 3, 4096) @ L.double().T).reshape(bs, 3, 64, 64)
     for gemm in GEMMS:
+        if gemm == "gemv" and bs * 3 > 16:
+            continue
         bn = bb.get_noise_v2(DEV, x, L, None, None, "GBN", "train", True, gemm=gemm)[1]
         err = (bn.double() - ref).abs().max().item()
-        assert err < (4e-6 if gemm == "tc" else ATOL), (gemm, err)
+        assert err < (4e-6 if gemm in ("tc", "gemv") else ATOL), (gemm, err)
 
 
 # ------------------------------------------------------------------ training-side fusion
 @pytest.mark.parametrize("gemm", GEMMS)
 @pytest.mark.parametrize("res,bs,C,noise_type", [(64, 6, 3, "gaussianBN"), (64, 64, 3, "gaussianBN"), (32, 4, 4, "gaussianBN"),
-                                                 (128, 2, 3, "gaussianBN"), (64, 5, 3, "GBN")])
+                                                 (128, 2, 3, "gaussianBN"), (64, 5, 3, "GBN"), (64, 4, 3, "gaussianBN"),
+                                                 (128, 32, 3, "gaussianBN"), (32, 64, 4, "gaussianBN"), (64, 16, 4, "gaussianBN"),
+                                                 (128, 1, 3, "gaussianBN")])
 def test_get_noise_train_equals_the_torch_sequence(res, bs, C, noise_type, gemm, L_dev):
+    _skip_wide_gemv(gemm, _cols(res, bs, C))
+    if gemm == "simt" and _cols(res, bs, C) > 300:
+        pytest.skip("the fp32 witness kernel is covered at smaller sizes")
     """x_alpha / tar1 / tar2 from the fused epilogue == the reference's expressions (iadb_bn.py:915,949-950)
     applied to this library's own (x0, bn, wn) for the same draw, bit for bit."""
     g = torch.Generator(device="cpu").manual_seed(res + bs)
