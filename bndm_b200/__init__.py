@@ -15,7 +15,7 @@ include/bndm_b200.h); there is no CPU fallback.
 """
 from ._lib import BndmError, LIB_PATH  # noqa: F401
 from .noise import CovMatL, get_noise, get_noise_train, get_noise_v2, prepare_L  # noqa: F401
-from .sampler import (IADBScheduler, IadbSampler, IadbStepper, iadb_step, sample_iadb,  # noqa: F401
+from .sampler import (GraphedModel, IADBScheduler, IadbSampler, IadbStepper, iadb_step, sample_iadb,  # noqa: F401
                       sample_iadb_conditional, sample_latent_iadb)
 from .ddim import DDIMScheduler, sample_ddim  # noqa: F401
 from .schedules import get_scheduler, get_scheduler_gamma, iadb_table  # noqa: F401

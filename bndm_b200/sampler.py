@@ -141,6 +141,42 @@ class GraphedStep:
                 events[1].record()
 
 
+class GraphedModel:
+    """``model(x, t)`` for one fixed input shape replayed from a CUDA graph (north_star: "the UNet2DModel forward ...
+    wrapped with CUDA Graphs per fixed shape").  Keeps the diffusers call conventions -- ``(x, t).sample`` and
+    ``(x, t, return_dict=False)[0]`` -- for loops that cannot be captured as a whole (DDIM with eta > 0 draws fresh
+    variance noise through the host every step).  The returned tensor is the graph's static output buffer: consume it
+    before the next call."""
+
+    def __init__(self, model, shape, device="cuda", t_dtype=torch.float32, warmup=2):
+        self.device = torch.device(device)
+        self.x = torch.zeros(tuple(shape), dtype=torch.float32, device=self.device)
+        self.t = torch.zeros(shape[0], dtype=t_dtype, device=self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.no_grad():
+            with torch.cuda.stream(side):
+                for _ in range(warmup):                       # lazy inits (cuDNN plans, workspaces) outside capture
+                    model(self.x, self.t, return_dict=False)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            with torch.cuda.graph(self.graph, stream=side):
+                self.out = model(self.x, self.t, return_dict=False)[0]
+        self.in_channels = getattr(model, "in_channels", shape[1])
+        self.out_channels = getattr(model, "out_channels", None)
+
+    def __call__(self, sample, timestep, return_dict=True):
+        self.x.copy_(_lib.require_cuda_f32(sample, "sample"))
+        if torch.is_tensor(timestep):
+            self.t.copy_(timestep.to(self.t.dtype).expand_as(self.t) if timestep.dim() == 0 else timestep.to(self.t.dtype))
+        else:
+            self.t.fill_(timestep)
+        self.graph.replay()
+        if not return_dict:
+            return (self.out,)
+        return SimpleNamespace(sample=self.out)
+
+
 def _call_model_iadb(model):
     return lambda x, t: model(x, t, return_dict=False)[0]
 
