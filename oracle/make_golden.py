@@ -92,5 +92,50 @@ def main():
         print("wrote", name, len(snaps))
 
 
+def tiny_unet():
+    """The UNet of the end-to-end ladder fixture: same block types as the reference's configs (iadb_bn.py:205-228) at
+    two levels, in 3 / out 6, ~6 M parameters, deterministic init (torch.manual_seed(0), CPU)."""
+    from bndm_b200.unet import UNet2DModel
+    torch.manual_seed(0)
+    return UNet2DModel(block_out_channels=(128, 128), in_channels=3, out_channels=6, layers_per_block=1,
+                       down_block_types=("DownBlock2D", "AttnDownBlock2D"), up_block_types=("AttnUpBlock2D", "UpBlock2D")).eval()
+
+
+def state_sha(model):
+    h = hashlib.sha256()
+    for k, v in sorted(model.state_dict().items()):
+        h.update(k.encode())
+        h.update(v.detach().cpu().numpy().tobytes())
+    return h.hexdigest()[:16]
+
+
+def ladder_e2e():
+    """Parity ladder step 4: the UNMODIFIED reference end to end on the CPU -- get_noise_v2 (inplace, per-sample
+    gamma) -> utils.sample_iadb with a real (small) UNet, fp32 -- stored with its inputs; the GPU test replays it through
+    the product (K1, the stock and the fused UNet, K2, eager and graphed)."""
+    get_noise_v2, _, ref_utils = load_reference()
+    L = hashed_tril(seed=0)
+    sha = hashlib.sha256(L.tobytes()).hexdigest()[:16]
+    rs = np.random.RandomState(4242)
+    white = rs.randn(2, 3, 64, 64).astype(np.float32)
+    gamma = np.array([1.0, 0.55], np.float32)
+    model = tiny_unet()
+    T, params = 6, (1000.0, 0.0, 3.0)
+    with torch.no_grad():
+        x0, bn, wn = get_noise_v2(torch.device("cpu"), torch.from_numpy(white.copy()), torch.from_numpy(L), torch.from_numpy(gamma),
+                                  None, "gaussianBN", "test", True)
+        x, x_all, _ = ref_utils.sample_iadb(model, x0, T, "sigmoid", params, 6, "gaussianBN", "test")
+        d_first = model(x0, torch.full((2,), 1.0), return_dict=False)[0]
+    np.savez_compressed(os.path.join(OUT, "ladder_e2e_tiny_unet.npz"), white=white, gamma=gamma, x0=x0.numpy(), x=x.numpy(),
+                        snaps=torch.stack(x_all).numpy(), d_first=d_first.numpy(), nb_step=T,
+                        scheduler_params=np.array(params, np.float64), L_sha=sha, model_sha=state_sha(model))
+    print("wrote ladder_e2e_tiny_unet", x.shape, "model", state_sha(model))
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "ladder":
+        ladder_e2e()
+    else:
+        main()
+        ladder_e2e()

@@ -270,7 +270,7 @@ def test_fused_unet_matches_plain_unet():
     assert got.shape == want.shape
     scale = want.abs().max().item()
     # same cuDNN TF32 convolutions (possibly other algorithms in NHWC) + fp32 round-off of the norms
-    assert (got - want).abs().max().item() < 2e-2 * scale, ((got - want).abs().max().item(), scale)
+    assert (got - want).abs().max().item() < 5e-3 * scale, ((got - want).abs().max().item(), scale)
     assert torch.equal(got, again)
 
 
@@ -302,7 +302,7 @@ def test_fused_unet_res128_matches_plain():
         want = model(x, t, return_dict=False)[0]
         got = fused(x, t, return_dict=False)[0]
     scale = want.abs().max().item()
-    assert (got - want).abs().max().item() < 2e-2 * scale
+    assert (got - want).abs().max().item() < 5e-3 * scale
 
 
 @pytest.mark.parametrize("B,C,Cd,H", [(5, 3, 6, 64), (3, 4, 8, 32), (2, 3, 3, 16)])
