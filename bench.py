@@ -362,7 +362,7 @@ def run_ours(args):
         sched.set_timesteps(T)
         ddim_gammas = [torch.full((B,), min(1.0, float(t) / 1000.0), device=dev) for t in sched.timesteps]
         from bndm_b200.sampler import GraphedModel
-        gmodel = GraphedModel(model, (B, C, RES, RES), device=dev)
+        gmodel = GraphedModel(model, (B, C, RES, RES), device=dev, uniform_timestep=True)
 
         def blue_variance(i, t, x):
             return bb.get_noise_v2(dev, x, handle, ddim_gammas[i], None, "gaussianBN", "test", False, want=("noise",))[0]

@@ -50,6 +50,7 @@ SIGNATURES = {
     "bndm_upsample2x_nhwc_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_attention_small_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_add_bias_nhwc_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
+    "bndm_snapshot_uint8_hwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
     "bndm_to_uint8_nhwc": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
 }
 
@@ -77,7 +78,7 @@ def load():
                 fn = getattr(lib, name)
                 fn.restype = res
                 fn.argtypes = args
-            if lib.bndm_version() != 1:
+            if lib.bndm_version() != 2:
                 raise BndmError("libbndm_b200.so ABI version mismatch")
             _lib = lib
     return _lib

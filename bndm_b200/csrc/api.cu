@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <new>
 
 #include "../../include/bndm_b200.h"
@@ -78,6 +79,11 @@ struct bndm_L {
   int profile = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   int ev_valid = 0;
+  // one workspace per handle: calls are serialised (host threads: mutex; streams: event hand-over)
+  std::mutex mu;
+  cudaStream_t last_stream = nullptr;
+  int has_last = 0;
+  cudaEvent_t xstream = nullptr;
 };
 
 static const int kMaxTileCounters = 4096;
@@ -155,6 +161,8 @@ static int alloc_ws(bndm_L *h, int max_columns) {
   h->ws_bytes = (int64_t)(3 * zb + pe * sizeof(float));
   return BNDM_OK;
 }
+
+static int reserve_unlocked(bndm_L *h, int max_columns, void *stream);
 
 // K1g set-up for table k = 2 res32 + dense: host row schedule -> device, then L gathered into stream order.
 // Leaves gv_sched[k] null (K1g unavailable, K1b takes over) when the quads do not fit the device's SMs.
@@ -249,12 +257,21 @@ int bndm_prepare_L(const float *L_dev, int n, int max_columns, void *stream, bnd
 
 int bndm_reserve_columns(bndm_L *h, int max_columns, void *stream) {
   if (!h) { set_error("null handle"); return BNDM_ERR_ARG; }
+  std::lock_guard<std::mutex> lock(h->mu);
+  return reserve_unlocked(h, max_columns, stream);
+}
+
+}  // extern "C"
+
+static int reserve_unlocked(bndm_L *h, int max_columns, void *stream) {
   if (max_columns <= h->req_cols) return BNDM_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (stream_is_capturing(s)) { set_error("workspace growth requested during stream capture"); return BNDM_ERR_WORKSPACE; }
   CK(cudaStreamSynchronize(s));
   return alloc_ws(h, max_columns);
 }
+
+extern "C" {
 
 int bndm_L_is_lower_triangular(const bndm_L *h) { return h ? h->lower_triangular : 0; }
 int64_t bndm_workspace_bytes(const bndm_L *h) { return h ? h->ws_bytes : 0; }
@@ -294,6 +311,7 @@ int bndm_free_L(bndm_L *h) {
   if (!h) return BNDM_OK;
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->xstream) cudaEventDestroy(h->xstream);
   free_ws(h);
   cudaFree(h->Lt);
   cudaFree(h->Lt_dense);
@@ -319,6 +337,24 @@ static int get_noise_impl(bndm_L *h, const float *z, const float *gamma, float *
   else if (res == 128) mode = kRes128;
   else { set_error("bndm_get_noise_f32: resolution %d not implemented (32/64/128)", res); return BNDM_ERR_UNSUPPORTED; }
   cudaStream_t s = (cudaStream_t)stream;
+  std::lock_guard<std::mutex> lock(h->mu);
+  if (h->has_last && h->last_stream != s) {
+    // the previous call used another stream and may still be running on the shared workspace: this stream waits
+    // for everything submitted there so far
+    if (stream_is_capturing(h->last_stream)) {
+      set_error("bndm_L handle used on a second stream while its previous stream is being captured (one handle owns one workspace)");
+      return BNDM_ERR_WORKSPACE;
+    }
+    if (!stream_is_capturing(s)) {
+      if (!h->xstream) CK(cudaEventCreateWithFlags(&h->xstream, cudaEventDisableTiming));
+      CK(cudaEventRecord(h->xstream, h->last_stream));
+      CK(cudaStreamWaitEvent(s, h->xstream, 0));
+    }
+    // (a capture starting on another stream cannot wait for work outside it: the capture protocol already requires
+    // the caller to have ordered earlier work before the capturing stream, e.g. side.wait_stream(current))
+  }
+  h->last_stream = s;
+  h->has_last = 1;
   const int src_is_image = (flags & BNDM_SRC_IMAGE) ? 1 : 0;
   // Sharded call: z is the GLOBAL white field.  Only the 128^2 image source couples samples across the batch
   // (tile n = k*Bg + b is re-read as (b', k') = divmod(n, 4), get_noise_recent.py:131-146): there the gather kernel
@@ -354,7 +390,7 @@ static int get_noise_impl(bndm_L *h, const float *z, const float *gamma, float *
     const int nbg = tc_pick_nb(n_cols);
     const int n_cols_pad_g = (n_cols + nbg - 1) / nbg * nbg;
     if (gather && n_cols_pad_g > h->cap_cols) {
-      int rc = bndm_reserve_columns(h, n_cols, stream);
+      int rc = reserve_unlocked(h, n_cols, stream);
       if (rc != BNDM_OK) return rc;
     }
     if ((reinterpret_cast<uintptr_t>(z) % 16) != 0) { set_error("bndm_get_noise_f32: z must be 16-byte aligned"); return BNDM_ERR_ARG; }
@@ -412,7 +448,7 @@ static int get_noise_impl(bndm_L *h, const float *z, const float *gamma, float *
   const StreamK sk = make_streamk(n_row_tiles, dense, n_cols_pad / nb, tc_num_sms(), tc_sub(nb, raw));   // tcgen05 path
   const size_t need = simt ? (size_t)sched.n_units() * n_cols_pad * kBlk : (size_t)sk.n_slots() * nb * kBlk;
   if (n_cols_pad > h->cap_cols || need > h->cap_partial) {
-    int rc = bndm_reserve_columns(h, n_cols > h->req_cols ? n_cols : h->req_cols + 1, stream);
+    int rc = reserve_unlocked(h, n_cols > h->req_cols ? n_cols : h->req_cols + 1, stream);
     if (rc != BNDM_OK) return rc;
     if (n_cols_pad > h->cap_cols || need > h->cap_partial) {
       set_error("internal: workspace still too small after growth (cols %d, partial %zu)", n_cols_pad, need);
@@ -777,6 +813,14 @@ int bndm_groupnorm_nhwc_f32(const float *x, const float *x2, int C1, const float
   cudaError_t e = launch_groupnorm_nhwc(x, x2, C1, res, add_bc, add_bc_stride, weight, bias, sum_out, y, B, C, HW, groups, eps, apply_silu, (cudaStream_t)stream);
   if (e == cudaErrorInvalidValue) { set_error("groupnorm: unsupported shape C=%d groups=%d", C, groups); return BNDM_ERR_UNSUPPORTED; }
   CK(e);
+  return BNDM_OK;
+}
+
+int bndm_snapshot_uint8_hwc(const float *x, uint8_t *out, int N, int C, int H, int W, const int *final_flags, int final_all,
+                            void *stream) {
+  if (!x || !out || N < 1 || C < 1 || H < 1 || W < 1) { set_error("snapshot_uint8: bad argument"); return BNDM_ERR_ARG; }
+  if ((int64_t)C * H * W >= ((int64_t)1 << 31)) { set_error("snapshot_uint8: image too large"); return BNDM_ERR_ARG; }
+  CK(launch_snapshot_u8(x, out, N, C, H * W, final_flags, final_all, (cudaStream_t)stream));
   return BNDM_OK;
 }
 

@@ -278,6 +278,8 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
                                   const float *bias, float *sum_out, float *y, int B, int C, int HW, int groups, float eps,
                                   int silu, cudaStream_t s);
 cudaError_t launch_to_u8(const float *x, uint8_t *out, int B, int C, int HW, cudaStream_t s);
+cudaError_t launch_snapshot_u8(const float *x, uint8_t *out, int N, int C, int HW, const int *final_flags, int final_all,
+                               cudaStream_t s);
 
 // ---- tf32 split (round-to-nearest-away hi, residual lo) -----------------------------------
 __device__ __forceinline__ float tf32_rna(float v) {

@@ -36,8 +36,16 @@ __device__ __forceinline__ int step_from_ticket(int *state, bool &publishes) {
   if (threadIdx.x == 0) s_ticket = atomicAdd(&state[0], 1);
   __syncthreads();
   const int ticket = s_ticket;
-  const int step = ticket / (int)gridDim.x;
+  int step = ticket / (int)gridDim.x;
   publishes = (ticket - step * (int)gridDim.x) == (int)gridDim.x - 1;
+  // state[1] = number of rows in the schedule table (0: unchecked).  A launch beyond the table (step_ called more
+  // than T times without a reset, a replay loop that runs too long) re-uses the last row instead of reading past
+  // the end, and raises the overrun flag the host can poll.
+  const int n_rows = state[1] & 0x3FFFFFFF;
+  if (n_rows > 0 && step >= n_rows) {
+    step = n_rows - 1;
+    if (threadIdx.x == 0 && publishes) atomicOr(&state[1], 0x40000000);
+  }
   return step;
 }
 
@@ -255,6 +263,55 @@ __global__ void __launch_bounds__(256) to_u8_kernel(const float *__restrict__ x,
       out[idx * C + c] = (uint8_t)__float2int_rn(__fmul_rn(v, 255.0f));   // torch.round = half-to-even
     }
   }
+}
+
+// ---- the IADB test driver's PNG conversion (iadb_bn.py:796-816): one CTA per (C,H,W) image ------------------
+//   final image:            v = clamp((x + 1) / 2, 0, 1)
+//   intermediate snapshot:  v = (x - min(x)) / (max(x) - min(x))      (min / max over the whole image)
+//   out[h][w][c] = (uint8)(v * 255)      numpy's astype(uint8): TRUNCATION (ddim_diffusers.py:687-688 rounds: K4 above)
+// The image is read twice (the second pass hits L2); min / max by warp shuffles + one shared-memory round.
+__global__ void __launch_bounds__(1024) snapshot_u8_kernel(const float *__restrict__ x, uint8_t *__restrict__ out, int C, int HW,
+                                                           const int *__restrict__ final_flags, int final_all) {
+  const int n = blockIdx.x;
+  const float *xi = x + (int64_t)n * C * HW;
+  const int total = C * HW;
+  const bool fin = final_flags ? final_flags[n] != 0 : final_all != 0;
+  float mn = 0.f, range = 1.f;
+  if (!fin) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+      const float v = xi[i];
+      lo = fminf(lo, v);
+      hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    __shared__ float s_lo[32], s_hi[32];
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    lo = s_lo[0]; hi = s_hi[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+    mn = lo;
+    range = __fsub_rn(hi, lo);
+  }
+  uint8_t *oi = out + (int64_t)n * C * HW;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {        // i = hw * C + c (output order)
+    const int hw = i / C, c = i - hw * C;
+    const float v0 = xi[(int64_t)c * HW + hw];
+    float v;
+    if (fin) v = fminf(fmaxf(__fdiv_rn(__fadd_rn(v0, 1.0f), 2.0f), 0.0f), 1.0f);
+    else v = __fdiv_rn(__fsub_rn(v0, mn), range);
+    oi[i] = (uint8_t)__float2int_rz(__fmul_rn(v, 255.0f));
+  }
+}
+
+cudaError_t launch_snapshot_u8(const float *x, uint8_t *out, int N, int C, int HW, const int *final_flags, int final_all,
+                               cudaStream_t s) {
+  snapshot_u8_kernel<<<N, 1024, 0, s>>>(x, out, C, HW, final_flags, final_all);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_to_u8(const float *x, uint8_t *out, int B, int C, int HW, cudaStream_t s) {

@@ -38,6 +38,7 @@ class DDIMScheduler:
         if beta_schedule != "linear" or prediction_type != "epsilon":
             raise NotImplementedError("only the configuration the reference uses (ddim_diffusers.py:499-503)")
         self.num_train_timesteps = num_train_timesteps
+        self.beta_start, self.beta_end = float(beta_start), float(beta_end)
         betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
         self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
         self.final_alpha_cumprod = torch.tensor(1.0)
@@ -134,27 +135,31 @@ def sample_ddim(model, x, num_inference_steps, eta=0.0, noise_fn=None, scheduler
     B = x_in.shape[0]
     ts = [int(t) for t in scheduler.timesteps]
 
+    uniform = getattr(model, "supports_uniform_timestep", False)     # one timestep for the whole batch (ddim_diffusers.py:679)
+
     def call(xx, tt):
-        out = model(xx, tt)
+        out = model(xx, tt, uniform_timestep=True) if uniform else model(xx, tt)
         return out.sample if hasattr(out, "sample") else out[0]
 
     seqs = []
     graph = None
     graphable = bool(use_graph) and eta == 0
     key = (id(model), tuple(x_in.shape), str(x_in.device), num_inference_steps, scheduler.num_train_timesteps,
-           bool(scheduler.clip_sample))
+           bool(scheduler.clip_sample), getattr(scheduler, "beta_start", None), getattr(scheduler, "beta_end", None))
     entry = _graph_cache.get(key) if graphable else None
     if entry is not None and entry["model_ref"]() is not model:       # id() reuse after garbage collection
         entry = None
     if entry is not None:
         x, table, state, t_vec, graph = entry["x"], entry["table"], entry["state"], entry["t_vec"], entry["graph"]
         x.copy_(x_in)
-        state.zero_()
+        state.copy_(entry["state0"])
         t_vec.fill_(float(ts[0]))
     else:
         x = x_in.clone()
         table = scheduler.coefficient_table(eta).to(x.device)
-        state = torch.zeros(2, dtype=torch.int32, device=x.device)
+        # {block tickets of the run, number of table rows}: K3 never reads past the table (bndm_b200.h)
+        state0 = torch.tensor([0, len(ts)], dtype=torch.int32, device=x.device)
+        state = state0.clone()
         t_vec = torch.full((B,), float(ts[0]), dtype=torch.float32, device=x.device)
         if graphable:
             side = torch.cuda.Stream(device=x.device)
@@ -164,18 +169,19 @@ def sample_ddim(model, x, num_inference_steps, eta=0.0, noise_fn=None, scheduler
                 for _ in range(2):
                     ddim_step_raw(x, x, call(x, t_vec), None, table, state, t_vec, scheduler.clip_sample)
             torch.cuda.current_stream(x.device).wait_stream(side)
-            x.copy_(keep); state.zero_(); t_vec.fill_(float(ts[0]))
+            x.copy_(keep); state.copy_(state0); t_vec.fill_(float(ts[0]))
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
                 ddim_step_raw(x, x, call(x, t_vec), None, table, state, t_vec, scheduler.clip_sample)
-            x.copy_(keep); state.zero_(); t_vec.fill_(float(ts[0]))
+            x.copy_(keep); state.copy_(state0); t_vec.fill_(float(ts[0]))
             try:
                 ref = weakref.ref(model)
             except TypeError:
                 ref = (lambda m: (lambda: m))(model)
             if len(_graph_cache) >= 4:
                 _graph_cache.pop(next(iter(_graph_cache)))
-            _graph_cache[key] = {"x": x, "table": table, "state": state, "t_vec": t_vec, "graph": graph, "model_ref": ref}
+            _graph_cache[key] = {"x": x, "table": table, "state": state, "state0": state0, "t_vec": t_vec, "graph": graph,
+                                 "model_ref": ref}
 
     for i, t in enumerate(ts):
         if graph is not None:

@@ -181,7 +181,7 @@ class FusedUNet2D(torch.nn.Module):
         pend = self._pending(blk, x.shape[1], x_bias, x2.shape[1] if x2 is not None else 0, x2_bias)
         y = groupnorm_silu_nhwc(x, blk.norm1, x2=x2, add_bc=pend["norm_add"])
         h = F.conv2d(y, blk.conv1.weight, None, padding=1)                 # bias folded into tb_all
-        y2 = groupnorm_silu_nhwc(h, blk.norm2, add_bc=tb_all[:, lo:hi])
+        y2 = groupnorm_silu_nhwc(h, blk.norm2, add_bc=tb_all[0, lo:hi] if tb_all.shape[0] == 1 else tb_all[:, lo:hi])
         h2 = F.conv2d(y2, blk.conv2.weight, None, padding=1)               # bias added with the residual (K6)
         if x2 is not None:
             w1, w2 = self._sc_split(blk, x.shape[1])
@@ -263,20 +263,30 @@ class FusedUNet2D(torch.nn.Module):
         return h, None
 
     kernels_per_forward = None      # K5 + K6 launches of one forward (set by the first call)
+    supports_uniform_timestep = True
 
     @torch.no_grad()
-    def forward(self, sample, timestep, return_dict=True):
+    def forward(self, sample, timestep, return_dict=True, uniform_timestep=False):
+        """``uniform_timestep``: the caller guarantees that every sample of the batch carries the SAME timestep (the
+        samplers do: iadb_bn.py:306 builds ``tt`` from one t, ddim_diffusers.py:679 passes a scalar).  The whole
+        time-embedding path -- sinusoid, two linears, SiLU and all 30 ``time_emb_proj`` projections -- then runs for
+        ONE row (five matrix-vector products instead of fp32 SIMT GEMMs over the batch) and K5 broadcasts the row."""
         m = self.m
         launches_before = LAUNCHES
         t = timestep
         if not torch.is_tensor(t):
             t = torch.tensor([t], dtype=torch.float32 if isinstance(t, float) else torch.int64, device=sample.device)
+            uniform_timestep = True
         elif t.dim() == 0:
             t = t[None].to(sample.device)
-        t = t * torch.ones(sample.shape[0], dtype=t.dtype, device=t.device)
+            uniform_timestep = True
+        if uniform_timestep:
+            t = t[:1]
+        else:
+            t = t * torch.ones(sample.shape[0], dtype=t.dtype, device=t.device)
         emb = timestep_embedding(t, m.time_proj_dim)
         temb_act = F.silu(m.time_embedding(emb))
-        temb_act = torch.addmm(self.temb_b, temb_act, self.temb_w.t())      # (B, sum of Cout): all projections
+        temb_act = torch.addmm(self.temb_b, temb_act, self.temb_w.t())      # (B or 1, sum of Cout): all projections
 
         # conv_in's bias is owed to h: the first resnet and the last skip consumer absorb it
         h = F.conv2d(sample.float().contiguous(memory_format=torch.channels_last), m.conv_in.weight, None, padding=1)

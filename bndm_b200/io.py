@@ -46,6 +46,27 @@ def to_uint8_nhwc(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def iadb_snapshots_uint8(samples: torch.Tensor, final) -> torch.Tensor:
+    """The same conversion for a stack of images ON THE DEVICE: (N,C,H,W) fp32 CUDA -> (N,H,W,C) uint8 CUDA, one kernel
+    (one CTA per image: min/max reduction + conversion; replaces 4-6 torch kernels and the D2H copy of every fp32
+    snapshot).  ``final``: bool for all images, or a length-N sequence / tensor (True = clamp((x+1)/2), False = min-max)."""
+    x = _lib.require_cuda_f32(samples, "samples")
+    if x.dim() != 4:
+        raise ValueError("samples must be (N, C, H, W)")
+    N, C, H, W = x.shape
+    flags = None
+    if not isinstance(final, bool):
+        flags = torch.as_tensor(final).to(torch.int32).reshape(-1).to(x.device)
+        if flags.numel() != N:
+            raise ValueError(f"final must have {N} entries")
+    out = torch.empty((N, H, W, C), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().bndm_snapshot_uint8_hwc(_lib.ptr(x), _lib.ptr(out), N, C, H, W, _lib.ptr(flags),
+                                                 1 if (isinstance(final, bool) and final) else 0, _lib.current_stream(x.device))
+    _lib.check(rc, "bndm_snapshot_uint8_hwc")
+    return out
+
+
 def iadb_snapshot_uint8(sample_chw: torch.Tensor, final: bool) -> np.ndarray:
     """(C,H,W) fp32 -> (H,W,C) uint8 exactly as iadb_bn.py's test driver writes its PNGs (:796-802, :814-816):
     the final image is ``clamp((x+1)/2, 0, 1)``, intermediate snapshots are min-max normalised, and the

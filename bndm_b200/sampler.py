@@ -50,27 +50,63 @@ def _expected_out_channels(noise_type, out_channel, C):
 class IadbStepper:
     """Device-resident schedule + K2 launcher for one sampling run of fixed shape."""
 
-    def __init__(self, table_cpu: torch.Tensor, first_t: float, batch: int, device):
+    def __init__(self, table_cpu: torch.Tensor, first_t, batch: int, device, expect_channels=None):
+        """``first_t``: the UNet timestep of the first step -- a float, or the (B,) vector the reference forms
+        (alpha_start per sample, iadb_bn.py:311).  ``expect_channels``: channel count the model output must have
+        (the reference fails with a shape error on anything else, iadb_bn.py:326-344)."""
         self.device = torch.device(device)
         if table_cpu.dim() != 3 or table_cpu.shape[1] != batch or table_cpu.shape[2] != 4:
             raise ValueError(f"schedule table must be (T, {batch}, 4), got {tuple(table_cpu.shape)}")
         self.n_steps = table_cpu.shape[0]
         self.table = table_cpu.to(self.device).contiguous()
-        self.state = torch.zeros(2, dtype=torch.int32, device=self.device)       # {step index, blocks done}
-        self.t_vec = torch.full((batch,), first_t, dtype=torch.float32, device=self.device)
-        self._first_t = first_t
+        # {block tickets of the run, number of table rows}: K2 never reads past the table (see bndm_b200.h)
+        self._state0 = torch.tensor([0, self.n_steps], dtype=torch.int32, device=self.device)
+        self.state = self._state0.clone()
+        first = torch.as_tensor(first_t, dtype=torch.float32).reshape(-1)
+        self._first_t = (first.expand(batch) if first.numel() == 1 else first).contiguous().to(self.device)
+        if self._first_t.numel() != batch:
+            raise ValueError(f"first_t must be a scalar or have {batch} entries")
+        self.t_vec = self._first_t.clone()
+        self.expect_channels = expect_channels
+        self._issued = 0          # steps issued since reset (host side; replays of a captured step count too)
+        self._nhwc = None         # kernel variant of this run (the grid size enters the device-side step index)
 
     def reset(self):
-        self.state.zero_()
-        self.t_vec.fill_(self._first_t)
+        self.state.copy_(self._state0)
+        self.t_vec.copy_(self._first_t)
+        self._issued = 0
+        self._nhwc = None
+
+    @property
+    def overrun(self) -> bool:
+        """True if a step was launched past the end of the schedule since the last reset (device-side flag)."""
+        return bool(int(self.state[1].item()) & 0x40000000)
+
+    def note_step(self, n=1):
+        self._issued += n
+        if self._issued > self.n_steps:
+            raise RuntimeError(f"IadbStepper: step {self._issued} of a {self.n_steps}-step schedule -- call reset() "
+                               f"before starting another run")
 
     def step_(self, x: torch.Tensor, d: torch.Tensor):
         """x <- x + dalpha*d[:, :C] (+ dgamma*d[:, C:]) in place; advances t_vec / state."""
         B, C = x.shape[0], x.shape[1]
         lib = _lib.load()
+        if not (isinstance(d, torch.Tensor) and d.dim() == 4 and d.shape[0] == B and d.shape[2:] == x.shape[2:]):
+            raise ValueError(f"model output {tuple(getattr(d, 'shape', ()))} does not match x {tuple(x.shape)}")
+        if self.expect_channels is not None and d.shape[1] != self.expect_channels:
+            raise ValueError(f"model output has {d.shape[1]} channels, the schedule expects {self.expect_channels} "
+                             f"(iadb_bn.py:326-344 fails on this shape)")
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise ValueError("x must be a contiguous float32 CUDA tensor (updated in place)")
+        self.note_step()
         # the channels-last UNet evaluation hands over d in NHWC memory: consumed in place
-        nhwc = (isinstance(d, torch.Tensor) and d.is_cuda and d.dtype == torch.float32 and d.dim() == 4 and not d.is_contiguous()
+        nhwc = (d.is_cuda and d.dtype == torch.float32 and not d.is_contiguous()
                 and d.is_contiguous(memory_format=torch.channels_last))
+        if self._nhwc is None:
+            self._nhwc = nhwc
+        elif self._nhwc != nhwc:
+            raise RuntimeError("model output changed memory format within a run (the step kernel variant is fixed per run)")
         if not nhwc:
             d = _lib.require_cuda_f32(d, "model output")
         fn = lib.bndm_iadb_step_sched_dnhwc_f32 if nhwc else lib.bndm_iadb_step_sched_f32
@@ -89,7 +125,13 @@ def iadb_step(x, d, dalpha, dgamma=None, out=None):
     dalpha = _lib.require_cuda_f32(dalpha.reshape(-1), "dalpha")
     if dgamma is not None:
         dgamma = _lib.require_cuda_f32(dgamma.reshape(-1), "dgamma")
-    out = torch.empty_like(x) if out is None else out
+    if d.shape[0] != x.shape[0] or d.shape[2:] != x.shape[2:]:
+        raise ValueError(f"d {tuple(d.shape)} does not match x {tuple(x.shape)}")
+    if out is None:
+        out = torch.empty_like(x)
+    elif not (isinstance(out, torch.Tensor) and out.is_cuda and out.device == x.device and out.dtype == torch.float32
+              and out.is_contiguous() and out.shape == x.shape):
+        raise ValueError("out must be a contiguous float32 CUDA tensor shaped like x on x's device")
     B, C = x.shape[0], x.shape[1]
     with torch.cuda.device(x.device):
         rc = _lib.load().bndm_iadb_step_f32(_lib.ptr(out), _lib.ptr(x), _lib.ptr(d), _lib.ptr(dalpha), _lib.ptr(dgamma),
@@ -132,6 +174,8 @@ class GraphedStep:
         stepper.reset()
 
     def replay(self, events=None):
+        if self.fused:
+            self.stepper.note_step()          # the captured K2 advances the device-side step index
         self.graph.replay()
         if not self.fused:
             if events is not None:
@@ -148,8 +192,10 @@ class GraphedModel:
     variance noise through the host every step).  The returned tensor is the graph's static output buffer: consume it
     before the next call."""
 
-    def __init__(self, model, shape, device="cuda", t_dtype=torch.float32, warmup=2):
+    def __init__(self, model, shape, device="cuda", t_dtype=torch.float32, warmup=2, uniform_timestep=False):
+        """``uniform_timestep``: the loop passes one timestep for the whole batch (see FusedUNet2D.forward)."""
         self.device = torch.device(device)
+        kw = {"uniform_timestep": True} if (uniform_timestep and getattr(model, "supports_uniform_timestep", False)) else {}
         self.x = torch.zeros(tuple(shape), dtype=torch.float32, device=self.device)
         self.t = torch.zeros(shape[0], dtype=t_dtype, device=self.device)
         self.graph = torch.cuda.CUDAGraph()
@@ -158,14 +204,14 @@ class GraphedModel:
         with torch.no_grad():
             with torch.cuda.stream(side):
                 for _ in range(warmup):                       # lazy inits (cuDNN plans, workspaces) outside capture
-                    model(self.x, self.t, return_dict=False)
+                    model(self.x, self.t, return_dict=False, **kw)
             torch.cuda.current_stream(self.device).wait_stream(side)
             with torch.cuda.graph(self.graph, stream=side):
-                self.out = model(self.x, self.t, return_dict=False)[0]
+                self.out = model(self.x, self.t, return_dict=False, **kw)[0]
         self.in_channels = getattr(model, "in_channels", shape[1])
         self.out_channels = getattr(model, "out_channels", None)
 
-    def __call__(self, sample, timestep, return_dict=True):
+    def __call__(self, sample, timestep, return_dict=True, uniform_timestep=False):
         self.x.copy_(_lib.require_cuda_f32(sample, "sample"))
         if torch.is_tensor(timestep):
             self.t.copy_(timestep.to(self.t.dtype).expand_as(self.t) if timestep.dim() == 0 else timestep.to(self.t.dtype))
@@ -177,7 +223,11 @@ class GraphedModel:
         return SimpleNamespace(sample=self.out)
 
 
-def _call_model_iadb(model):
+def _call_model_iadb(model, uniform_timestep=False):
+    """``uniform_timestep``: every sample of a step carries the same UNet timestep (true for the reference's loops);
+    evaluators that can exploit it (FusedUNet2D) are told so."""
+    if uniform_timestep and getattr(model, "supports_uniform_timestep", False):
+        return lambda x, t: model(x, t, return_dict=False, uniform_timestep=True)[0]
     return lambda x, t: model(x, t, return_dict=False)[0]
 
 
@@ -193,7 +243,8 @@ class IadbSampler:
 
     def __init__(self, model, shape, nb_step, scheduler_gamma="sigmoid", scheduler_params=(1000.0, 0.0, 3.0),
                  out_channel=6, noise_type="gaussianBN", scheduler_alpha="linear", alpha_param=1000.0, x_c=None,
-                 device="cuda", graph="step", time_step_kernel=False, table=None, first_t=None):
+                 device="cuda", graph="step", time_step_kernel=False, table=None, first_t=None, schedule_device="cpu",
+                 schedule_nb_steps=None):
         self.device = torch.device(device)
         self.shape = tuple(shape)
         B, C = self.shape[0], self.shape[1]
@@ -201,18 +252,29 @@ class IadbSampler:
         if table is None:
             _expected_out_channels(noise_type, out_channel, C)
             table, first_t = iadb_table(nb_step, scheduler_alpha, scheduler_gamma,
-                                        tuple(float(p) for p in scheduler_params), alpha_param, batch=B)
+                                        tuple(float(p) for p in scheduler_params), alpha_param, batch=B,
+                                        device=schedule_device, schedule_nb_steps=schedule_nb_steps)
         else:
             table = table.clone()
-        if not (noise_type in TWO_HEAD and out_channel == 2 * C):
+        two = noise_type in TWO_HEAD and out_channel == 2 * C
+        if not two:
             table[..., 1] = 0.0
-        self.stepper = IadbStepper(table, first_t, B, self.device)
+        self.stepper = IadbStepper(table, first_t, B, self.device, expect_channels=2 * C if two else C)
         self.x = torch.zeros(self.shape, dtype=torch.float32, device=self.device)
-        call = _call_model_iadb(model)
+        # the UNet timestep of a step is alpha_start of ONE t for the whole batch (iadb_bn.py:306-311); with the
+        # non-linear alpha schedules torch's CPU vector / scalar paths may differ in the last ulp across the batch, so
+        # the hint is only given when the table says the values really are identical
+        t_first = torch.as_tensor(first_t, dtype=torch.float32).reshape(-1)
+        uniform = bool((table[:, :, 2] == table[:, :1, 2]).all()) and bool((t_first == t_first[0]).all())
+        call = _call_model_iadb(model, uniform)
+        self.x_c = None
         if x_c is not None:
-            x_c = _lib.require_cuda_f32(x_c, "x_c")
-            inner = call
-            call = lambda xx, tt: inner(torch.cat([xx, x_c], 1), tt)          # iadb_bn.py:406
+            # a STATIC conditioning buffer: every run copies its x_c in, so a captured graph never closes over a
+            # caller tensor (new batch = new x_c = same graph) and never replays stale conditioning
+            self.x_c = torch.empty(tuple(x_c.shape), dtype=torch.float32, device=self.device)
+            self.x_c.copy_(x_c)
+            inner, buf = call, self.x_c
+            call = lambda xx, tt: inner(torch.cat([xx, buf], 1), tt)          # iadb_bn.py:406
         self.call = call
         try:
             self._model_ref = weakref.ref(model)
@@ -231,10 +293,14 @@ class IadbSampler:
         self.kernel_launches_per_run = nb_step            # K2 launches of one run (graph nodes count)
 
     @torch.no_grad()
-    def run(self, x0, on_step=None):
+    def run(self, x0, on_step=None, x_c=None):
         """x0 is copied into the static buffer (the reference never writes into x0,
         iadb_bn.py:326 makes new tensors); returns the static buffer (clone it to keep it)."""
         self.x.copy_(_lib.require_cuda_f32(x0, "x0"))
+        if x_c is not None:
+            if self.x_c is None:
+                raise ValueError("this sampler was built without conditioning")
+            self.x_c.copy_(x_c)
         self.stepper.reset()
         for i, t in enumerate(reversed(range(self.nb_step))):
             ev = self.events[i] if self.events is not None else None
@@ -266,17 +332,18 @@ _sampler_cache: "dict[tuple, IadbSampler]" = {}
 
 
 def _run_iadb(model, x0, x_c, nb_step, scheduler_alpha, scheduler_gamma, scheduler_params, out_channel, noise_type,
-              train_or_test, log_freq, use_graph, alpha_param=1000.0):
+              train_or_test, log_freq, use_graph, alpha_param=1000.0, schedule_device="cpu", schedule_nb_steps=None):
     x0 = _lib.require_cuda_f32(x0, "x0")
     params = tuple(float(p) for p in scheduler_params)
     key = (id(model), tuple(x0.shape), str(x0.device), nb_step, scheduler_alpha, scheduler_gamma, params, out_channel,
-           noise_type, float(alpha_param), None if x_c is None else x_c.data_ptr())
+           noise_type, float(alpha_param), None if x_c is None else tuple(x_c.shape), str(schedule_device), schedule_nb_steps)
     sampler = _sampler_cache.get(key) if use_graph else None
     if sampler is not None and sampler._model_ref() is not model:      # id() reuse after garbage collection
         sampler = None
     if sampler is None:
         sampler = IadbSampler(model, x0.shape, nb_step, scheduler_gamma, params, out_channel, noise_type,
-                              scheduler_alpha, alpha_param, x_c, x0.device, graph="step" if use_graph else None)
+                              scheduler_alpha, alpha_param, x_c, x0.device, graph="step" if use_graph else None,
+                              schedule_device=schedule_device, schedule_nb_steps=schedule_nb_steps)
         if use_graph:
             if len(_sampler_cache) >= 4:
                 _sampler_cache.pop(next(iter(_sampler_cache)))
@@ -292,19 +359,22 @@ def _run_iadb(model, x0, x_c, nb_step, scheduler_alpha, scheduler_gamma, schedul
         if train_or_test == "test" and (t % log_freq == 0 or t == nb_step - 1):
             x_all.append(x.clone())
         tic[0] = time.time()
-    x = sampler.run(x0, on_step).clone()
+    x = sampler.run(x0, on_step, x_c=x_c).clone()
     return x, x_all, per_step
 
 
-def sample_iadb(model, x0, nb_step, *args, use_graph=False, **kwargs):
+def sample_iadb(model, x0, nb_step, *args, use_graph=False, schedule_device="cpu", **kwargs):
     """Both reference signatures (see module docstring).  Test mode returns
-    ``(x, x_all, mean_step_seconds)`` like iadb_bn.py:376-378, otherwise ``x``."""
+    ``(x, x_all, mean_step_seconds)`` like iadb_bn.py:376-378, otherwise ``x``.
+    ``schedule_device``: where alpha / gamma are evaluated ('cpu' = the reference's CPU path, the default; pass
+    ``x0.device`` to reproduce a reference that runs its schedule kernels on the GPU, see schedules.iadb_table)."""
     if len(args) + len(kwargs) == 1:                  # iadb_bn.py:287 -- (scheduler_params,) + module `opt`
         scheduler_params = args[0] if args else kwargs["scheduler_params"]
         o = opt
         cfg = dict(scheduler_alpha=o.scheduler_alpha, scheduler_gamma=o.scheduler_gamma,
                    out_channel=o.out_channel, noise_type=o.noise_type, train_or_test=o.train_or_test,
-                   log_freq=25, alpha_param=getattr(o, "scheduler_param", 1000.0))
+                   log_freq=25, alpha_param=getattr(o, "scheduler_param", 1000.0),
+                   schedule_nb_steps=getattr(o, "nb_steps", nb_step))   # iadb_bn.py:107,165 divide by opt.nb_steps
     else:                                             # utils.py:180
         names = ("scheduler_gamma", "scheduler_params", "out_channel", "noise_type", "train_or_test", "scheduler_alpha")
         bound = dict(zip(names, args))
@@ -313,7 +383,7 @@ def sample_iadb(model, x0, nb_step, *args, use_graph=False, **kwargs):
         scheduler_params = bound.pop("scheduler_params")
         cfg = dict(bound, log_freq=1)
     x, x_all, per_step = _run_iadb(model, x0, None, nb_step, scheduler_params=scheduler_params, use_graph=use_graph,
-                                   **cfg)
+                                   schedule_device=schedule_device, **cfg)
     if cfg["train_or_test"] == "test":
         return x, x_all, (float(np.mean(per_step[1:])) if len(per_step) > 1 else float("nan"))
     return x
@@ -324,7 +394,7 @@ def sample_iadb_conditional(model, x0, x_c, nb_step, scheduler_params, *, use_gr
     o = opt
     x, x_all, _ = _run_iadb(model, x0, x_c, nb_step, o.scheduler_alpha, o.scheduler_gamma, scheduler_params,
                             o.out_channel, o.noise_type, o.train_or_test, 25, use_graph,
-                            getattr(o, "scheduler_param", 1000.0))
+                            getattr(o, "scheduler_param", 1000.0), schedule_nb_steps=getattr(o, "nb_steps", nb_step))
     if o.train_or_test == "test":
         return x, x_all
     return x

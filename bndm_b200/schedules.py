@@ -55,7 +55,7 @@ def get_scheduler_gamma(x, scheduler, scheduler_params, nb_steps):
 
 
 def iadb_table(nb_step, scheduler_alpha="linear", scheduler_gamma="sigmoid", scheduler_params=(1000.0, 0.0, 3.0),
-               alpha_param=1000.0, batch=1):
+               alpha_param=1000.0, batch=1, device="cpu", schedule_nb_steps=None):
     """(T,B,4) fp32 CPU table; row [r, b] <-> loop step t = T-1-r, sample b (iadb_bn.py:304-316):
     {alpha(t+1)-alpha(t), gamma(t+1)-gamma(t), alpha(t) [= the NEXT step's UNet timestep], 0}
     and the first UNet timestep alpha(T).
@@ -64,18 +64,27 @@ def iadb_table(nb_step, scheduler_alpha="linear", scheduler_gamma="sigmoid", sch
     (``tt = torch.randint(t, t + 1, (B,))``): torch's CPU kernels send short tensors and loop
     tails through scalar libm and full vectors through SLEEF, which differ in the last ulp, so
     the coefficient a sample gets depends on B and on its position in the batch.  Evaluating the
-    whole schedule as one (T,) tensor would be faster and is NOT bit-identical."""
+    whole schedule as one (T,) tensor would be faster and is NOT bit-identical.
+
+    ``device``: where the schedule expressions are evaluated.  The default 'cpu' pins the table to the reference's
+    CPU path (the golden vectors); pass the sampling device to reproduce a reference that itself runs on the GPU
+    (iadb_bn.py:306 moves ``tt`` to ``device`` first, and CPU / CUDA sigmoid differ in the last ulp, which for
+    tau = 1000 moves a per-step dgamma by up to a percent).  ``schedule_nb_steps``: the divisor of the schedules when
+    it is not the loop length -- iadb_bn.py's versions divide by the global ``opt.nb_steps`` (:107, :165), whatever
+    ``nb_step`` the loop was given.  Returns (table, first_t) with first_t the (B,) vector alpha(T) of the first step."""
+    n_div = nb_step if schedule_nb_steps is None else schedule_nb_steps
     rows = []
+    first_t = None
     for t in reversed(range(nb_step)):
-        tt = torch.full((batch,), t, dtype=torch.int64)
-        a_start = get_scheduler((tt + 1).float(), scheduler_alpha, nb_step, alpha_param)
-        a_end = get_scheduler(tt.float(), scheduler_alpha, nb_step, alpha_param)
-        g_start = get_scheduler_gamma((tt + 1).float(), scheduler_gamma, scheduler_params, nb_step)
-        g_end = get_scheduler_gamma(tt.float(), scheduler_gamma, scheduler_params, nb_step)
-        if not rows:
-            first_t = float(a_start[0])
+        tt = torch.full((batch,), t, dtype=torch.int64).to(device)
+        a_start = get_scheduler((tt + 1).float(), scheduler_alpha, n_div, alpha_param)
+        a_end = get_scheduler(tt.float(), scheduler_alpha, n_div, alpha_param)
+        g_start = get_scheduler_gamma((tt + 1).float(), scheduler_gamma, scheduler_params, n_div)
+        g_end = get_scheduler_gamma(tt.float(), scheduler_gamma, scheduler_params, n_div)
+        if first_t is None:
+            first_t = a_start.float().cpu().clone()
         rows.append(torch.stack([a_start - a_end, g_start - g_end, a_end, torch.zeros_like(a_end)], dim=1))
-    return torch.stack(rows).float().contiguous(), first_t
+    return torch.stack(rows).float().cpu().contiguous(), first_t
 
 
 def latent_table(num_inference_steps, batch=1):
@@ -88,4 +97,4 @@ def latent_table(num_inference_steps, batch=1):
         d = (t + 1) / N - t / N
         rows.append([d, d, t / N, 0.0])
     table = torch.tensor(rows, dtype=torch.float64).float()
-    return table[:, None, :].expand(N, batch, 4).contiguous(), float(torch.tensor(1.0 * N / N))
+    return table[:, None, :].expand(N, batch, 4).contiguous(), torch.full((batch,), float(torch.tensor(1.0 * N / N)))

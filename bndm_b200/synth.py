@@ -53,6 +53,26 @@ def blue_noise_L(fc: float = 0.35, p: float = 2.0, floor: float = 1e-3) -> np.nd
     return np.linalg.cholesky(blue_noise_sigma(fc, p, floor)).astype(np.float32)
 
 
+def red_noise_sigma(fc: float = 0.08, p: float = 2.0, floor: float = 1e-3) -> np.ndarray:
+    """Toroidal LOW-pass ("red") covariance on the 64x64 tile, the counterpart of ``blue_noise_sigma`` for
+    ``noise_type='gaussianRN'`` (iadb_bn.py:84-85 loads cov_gaussianRN_L_res64_d3.npz):
+    S(f) = max(floor, 1 / (1 + (|f|/fc)**2)**p), unit diagonal."""
+    f = np.fft.fftfreq(TILE)
+    fr = np.sqrt(f[:, None] ** 2 + f[None, :] ** 2)
+    S = np.maximum(floor, 1.0 / (1.0 + (fr / fc) ** 2) ** p)
+    c = np.real(np.fft.ifft2(S))
+    c /= c[0, 0]
+    yy, xx = np.divmod(np.arange(NPIX), TILE)
+    dy = (yy[:, None] - yy[None, :]) % TILE
+    dx = (xx[:, None] - xx[None, :]) % TILE
+    return c[dy, dx]
+
+
+def red_noise_L(fc: float = 0.08, p: float = 2.0, floor: float = 1e-3) -> np.ndarray:
+    """cholesky(red_noise_sigma(...)) in float64 -> fp32: a synthetic stand-in for the reference's RN factor."""
+    return np.linalg.cholesky(red_noise_sigma(fc, p, floor)).astype(np.float32)
+
+
 def empirical_covariance(fields):
     """(S, ...) samples of a random field (e.g. S blue-noise masks of 64x64, Gaussianised) -> (n,n) float64
     covariance of the flattened, mean-removed fields, on the samples' device (torch).  The reference ships only

@@ -176,6 +176,10 @@ class UNet2DModel(nn.Module):
                  block_out_channels=(224, 448, 672, 896), layers_per_block=2, act_fn="silu", attention_head_dim=8,
                  norm_num_groups=32, add_attention=True):
         super().__init__()
+        if norm_num_groups != 32:
+            # every block of this restatement is built with the diffusers default of 32 groups (the only value the
+            # reference's configs use, iadb_bn.py:205-282): refuse instead of silently ignoring another value
+            raise NotImplementedError("UNet2DModel: norm_num_groups other than 32 is not implemented")
         if act_fn != "silu":
             raise NotImplementedError("the reference only uses act_fn='silu' (iadb_bn.py:60,282)")
         if len(down_block_types) != len(up_block_types) or len(down_block_types) != len(block_out_channels):

@@ -14,7 +14,12 @@
  *   - return value: 0 = ok, negative = error (see enum); bndm_last_error() gives the text
  *     (thread-local); nothing throws or exits across the ABI;
  *   - the caller owns every buffer; the library retains no caller pointer past a call,
- *     except the L pointer bound into the opaque bndm_L handle (must outlive it).
+ *     except the L pointer bound into the opaque bndm_L handle (must outlive it);
+ *   - a bndm_L handle owns ONE workspace (gathered columns, operand copies, partial tiles): calls on the same
+ *     handle are serialised -- host threads by a mutex inside the handle, streams by an event the library inserts
+ *     when a call arrives on another stream than the previous one (a capturing stream relies on the capture
+ *     protocol's own ordering; a call on a second stream while the first is still being captured is refused with
+ *     BNDM_ERR_WORKSPACE).  Use one handle per stream for concurrent calls; handles are per device.
  */
 #ifndef BNDM_B200_H_
 #define BNDM_B200_H_
@@ -25,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BNDM_ABI_VERSION 1
+#define BNDM_ABI_VERSION 2
 
 enum {
   BNDM_OK = 0,
@@ -142,8 +147,10 @@ int bndm_iadb_step_f32(float *x_out, const float *x, const float *d, const float
  * The kernel also fills t_next_out[b] with its row's t_next (the next UNet "timestep" =
  * alpha_start of the following step, iadb_bn.py:311,319).
  * `state` is 2 ints on the device: state[0] counts block tickets over the run (a launch of G
- * blocks is step ticket / G), state[1] is reserved; zero both before the first step and keep
- * B, C, HW and the buffers' alignment fixed within a run (they determine G).                */
+ * blocks is step ticket / G); state[1] = T, the number of rows of `table` (0 = unchecked): a launch
+ * past the table re-uses the last row instead of reading beyond it and sets bit 30 of state[1]
+ * (overrun flag).  Before the first step of a run set state = {0, T}; keep B, C, HW, the buffers'
+ * alignment and the d layout fixed within a run (they determine G).                          */
 int bndm_iadb_step_sched_f32(float *x_out, const float *x, const float *d, const float *table,
                              int *state, float *t_next_out, int B, int C, int HW, int d_channels,
                              void *stream);
@@ -159,7 +166,7 @@ int bndm_iadb_step_sched_dnhwc_f32(float *x_out, const float *x, const float *d_
  *     out = (c[2]*x0 + c[3]*eps) [+ c[4]*noise]          (noise may be NULL => eta = 0)
  * coef: dev, rows of 8 floats {sqrt(abar_t), sqrt(1-abar_t), sqrt(abar_prev),
  * sqrt(1-abar_prev-sigma^2), sigma, t_next, 0, 0}; the row used is ticket / gridDim like the
- * scheduled IADB step (state[0] = run-long block-ticket counter, zero before the first step;
+ * scheduled IADB step (state = {run-long block-ticket counter, number of rows (0 = unchecked)} as there;
  * state == NULL => row 0).  t_next_out: dev [B] float or NULL.  n = B*C*H*W.  x_out may alias x. */
 int bndm_ddim_step_f32(float *x_out, const float *x, const float *eps, const float *noise,
                        const float *coef, int *state, float *t_next_out, int B, int clip, int64_t n,
@@ -226,6 +233,14 @@ int bndm_add_bias_nhwc_f32(const float *a, const float *a2, const float *bias_a,
 /* Image post-processing of the test drivers (iadb_bn.py:796-816, ddim_diffusers.py:687-688):
  * out_u8[b,h,w,c] = round(clamp(x[b,c,h,w]/2 + 0.5, 0, 1) * 255), NCHW fp32 -> NHWC uint8. */
 int bndm_to_uint8_nhwc(const float *x, uint8_t *out, int B, int C, int H, int W, void *stream);
+
+/* The IADB test driver's PNG conversion (iadb_bn.py:796-816) for N images x dev (N,C,H,W) -> out dev (N,H,W,C) uint8:
+ *   final image (final_flags[n] != 0, or final_all when final_flags == NULL):  v = clamp((x + 1) / 2, 0, 1)
+ *   intermediate snapshot:  v = (x - min) / (max - min), min / max over the whole image (:802)
+ *   out = (uint8)(v * 255)  -- numpy's astype(uint8), i.e. TRUNCATION (bndm_to_uint8_nhwc rounds, as ddim_diffusers.py does).
+ * Replaces 4-6 torch kernels + a D2H copy of the fp32 image per snapshot.  final_flags: dev int[N] or NULL.          */
+int bndm_snapshot_uint8_hwc(const float *x, uint8_t *out, int N, int C, int H, int W, const int *final_flags,
+                            int final_all, void *stream);
 
 #ifdef __cplusplus
 }

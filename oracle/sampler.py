@@ -75,7 +75,8 @@ def sample_iadb_opt(model, x0, nb_step, scheduler_params, opt):
     reference reads as a module global (:107,:311-316,:323-329,:364-373)."""
     return _iadb_loop(model, x0, None, nb_step, opt.scheduler_alpha, opt.scheduler_gamma,
                       scheduler_params, opt.out_channel, opt.noise_type, opt.train_or_test,
-                      log_freq=25, with_time=True, alpha_param=getattr(opt, "scheduler_param", 1000.0))
+                      log_freq=25, with_time=True, alpha_param=getattr(opt, "scheduler_param", 1000.0),
+                      schedule_nb_steps=getattr(opt, "nb_steps", nb_step))
 
 
 @torch.no_grad()
@@ -84,17 +85,21 @@ def sample_iadb_conditional(model, x0, x_c, nb_step, scheduler_params, opt):
     (x, x_all) in test mode -- no timing element (:436-437)."""
     return _iadb_loop(model, x0, x_c, nb_step, opt.scheduler_alpha, opt.scheduler_gamma,
                       scheduler_params, opt.out_channel, opt.noise_type, opt.train_or_test,
-                      log_freq=25, with_time=False, alpha_param=getattr(opt, "scheduler_param", 1000.0))
+                      log_freq=25, with_time=False, alpha_param=getattr(opt, "scheduler_param", 1000.0),
+                      schedule_nb_steps=getattr(opt, "nb_steps", nb_step))
 
 
 def _iadb_loop(model, x0, x_c, nb_step, scheduler_alpha, scheduler_gamma, scheduler_params,
-               out_channel, noise_type, train_or_test, log_freq, with_time, alpha_param=1000.0):
+               out_channel, noise_type, train_or_test, log_freq, with_time, alpha_param=1000.0, schedule_nb_steps=None):
+    # iadb_bn.py's get_scheduler / get_scheduler_gamma divide by the GLOBAL opt.nb_steps (:107, :165), whatever loop
+    # length the sampler was given; utils.py's take nb_steps as an argument (utils.py:110)
+    n_div = nb_step if schedule_nb_steps is None else schedule_nb_steps
     x = x0
     snaps, secs = [], []
     if nb_step == 1000:
         log_freq = 100
     for t in reversed(range(nb_step)):
-        a_s, a_e, g_s, g_e = _coefficients(t, x0.shape[0], x0.device, nb_step, scheduler_alpha,
+        a_s, a_e, g_s, g_e = _coefficients(t, x0.shape[0], x0.device, n_div, scheduler_alpha,
                                            scheduler_gamma, scheduler_params, alpha_param)
         inp = x if x_c is None else torch.cat([x, x_c], 1)
         tic = time.time()

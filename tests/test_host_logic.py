@@ -32,7 +32,7 @@ def test_library_builds_loads_and_exports_header_symbols():
         assert hasattr(lib, name), f"{name} declared in include/bndm_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(declared)
-    assert lib.bndm_version() == 1
+    assert lib.bndm_version() == 2
     assert lib.bndm_last_error() is not None
 
 
@@ -82,7 +82,7 @@ def test_iadb_table_rows_are_the_reference_differences(B, params):
     from oracle.sampler import _coefficients
     T = 250
     table, first = iadb_table(T, "linear", "sigmoid", params, batch=B)
-    assert table.shape == (T, B, 4) and first == 1.0
+    assert table.shape == (T, B, 4) and first.shape == (B,) and bool((first == 1.0).all())
     for row, t in enumerate(reversed(range(T))):
         a_s, a_e, g_s, g_e = _coefficients(t, B, "cpu", T, "linear", "sigmoid", params)
         assert torch.equal(table[row, :, 0], a_s - a_e) and torch.equal(table[row, :, 1], g_s - g_e)
@@ -93,7 +93,7 @@ def test_iadb_table_rows_are_the_reference_differences(B, params):
     assert abs(float(table[:, 0, 0].double().sum()) - 1.0) < 1e-6       # telescoping: sum d_alpha = 1
     lt, lfirst = latent_table(250, batch=B)
     assert lt.shape == (250, B, 4)
-    assert lfirst == 1.0 and float(lt[0, 0, 0]) == np.float32(250 / 250 - 249 / 250)
+    assert bool((lfirst == 1.0).all()) and float(lt[0, 0, 0]) == np.float32(250 / 250 - 249 / 250)
 
 
 def test_ddim_scheduler_tables_match_oracle():
@@ -205,8 +205,8 @@ def test_streamk_schedule_is_consistent():
 
 
 def test_gemv_row_schedule_covers_every_quad_once_and_is_balanced():
-    """K1g's row ownership (csrc/noise_gemv.cu): every needed quad of 4 rows belongs to exactly one CTA slot, row groups
-    are sorted longest first, and no CTA streams more than 2.5 % above the mean at the full triangular size."""
+    """K1g's row ownership (csrc/noise_gemv.cu): every needed quad of 4 rows belongs to exactly one CTA slot, slots are
+    sorted longest first, and no CTA streams more than 2.5 % above the mean at the full triangular size."""
     import ctypes as C
     from bndm_b200 import _lib
     lib = _lib.load()
@@ -344,3 +344,55 @@ def test_L_construction_from_a_covariance():
     np.testing.assert_allclose((L2.double() @ L2.double().T).numpy(), cov.numpy(), atol=1e-5)
     with pytest.raises(Exception):
         synth.cholesky_L(-torch.eye(4))
+
+
+def test_artefact_files_round_trip_in_the_reference_layout(tmp_path):
+    """The reference's on-disk artefacts: ./bluenoise/cov_gaussian{BN,RN}_L_res64_d3.npz with key 'x'
+    (iadb_bn.py:83-86) and <root>/noise/noise_batch{bs}_idx{:0>5}.npz with key 'noise' (iadb_bn.py:764,
+    ddim_diffusers.py:667-669): files written by the helpers load through the reference's own expressions and back."""
+    from bndm_b200 import io
+    from bndm_b200.synth import hashed_tril, save_L_npz
+    L = hashed_tril(seed=3)
+    blue = tmp_path / "bluenoise"
+    blue.mkdir()
+    save_L_npz(str(blue / "cov_gaussianBN_L_res64_d3.npz"), L)
+    save_L_npz(str(blue / "cov_gaussianRN_L_res64_d3.npz"), (L * np.float32(0.5)).astype(np.float32))
+    # the reference's loader, verbatim (iadb_bn.py:83-86)
+    ref_bn = np.load(str(blue / "cov_gaussianBN_L_res64_d3.npz"))["x"].astype(np.float32)
+    assert np.array_equal(ref_bn, L)
+    got_bn = io.load_cov_mat_L("gaussianBN", root=str(blue), device="cpu")
+    got_rn = io.load_cov_mat_L("gaussianRN", root=str(blue), device="cpu")
+    assert got_bn.dtype == torch.float32 and torch.equal(got_bn, torch.from_numpy(L))
+    assert torch.equal(got_rn, torch.from_numpy(L) * 0.5)
+    assert torch.equal(io.load_cov_mat_L("GBN", root=str(blue), device="cpu"), got_bn)       # everything but RN reads the BN file
+    save_L_npz(str(blue / "cov_gaussianBN_L_res64_d3.npz"), L[:100, :100])
+    with pytest.raises(ValueError):
+        io.load_cov_mat_L("gaussianBN", root=str(blue), device="cpu")
+
+    root = tmp_path / "run"
+    (root / "noise").mkdir(parents=True)
+    x0 = torch.randn(5, 3, 8, 8, dtype=torch.float64)                                        # np.random.randn is float64 (iadb_bn.py:761)
+    io.save_noise_batch(str(root), 5, 17, x0)
+    assert io.noise_batch_path(str(root), 5, 17).endswith("noise/noise_batch5_idx00017.npz")
+    # the reference's reader, verbatim (iadb_bn.py:764-766): np.load(...)['noise'] -> torch -> .float()
+    ref = torch.from_numpy(np.load(str(root / "noise" / "noise_batch5_idx00017.npz"))["noise"]).float()
+    got = io.load_noise_batch(str(root), 5, 17, device="cpu")
+    assert got.dtype == torch.float32 and torch.equal(got, ref) and torch.equal(got, x0.float())
+
+
+def test_synthetic_red_and_blue_factors_have_the_right_spectra():
+    """gaussianRN gets its own synthetic factor (low-pass), not the blue matrix: L L^T has unit diagonal and the power of
+    L.z sits at low frequencies for red, at high frequencies for blue (the figure script's check, fig script :31-36)."""
+    from bndm_b200.synth import blue_noise_L, red_noise_L
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal((4096, 24))
+    fy = np.fft.fftfreq(64)
+    fr = np.sqrt(fy[:, None] ** 2 + fy[None, :] ** 2)
+    ratios = {}
+    for name, L in (("red", red_noise_L()), ("blue", blue_noise_L())):
+        assert L.dtype == np.float32 and np.allclose(np.triu(L, 1), 0)
+        assert np.allclose((L.astype(np.float64) ** 2).sum(1), 1.0, atol=1e-4)               # unit-variance pixels
+        f = (L.astype(np.float64) @ z).T.reshape(24, 64, 64)
+        spec = (np.abs(np.fft.fft2(f)) ** 2).mean(0)
+        ratios[name] = spec[(fr > 0) & (fr < 0.1)].mean() / spec[fr > 0.35].mean()
+    assert ratios["red"] > 20 and ratios["blue"] < 0.2, ratios

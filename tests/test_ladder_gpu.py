@@ -97,3 +97,19 @@ def test_fused_unet_vs_stock_with_tf32(which):
         got = fused(x, t, return_dict=False)[0]
     scale = max(1.0, want.abs().max().item())
     assert (got - want).abs().max().item() <= 5e-3 * scale
+
+
+@pytest.mark.parametrize("which", ["cat_res64", "latent512"])
+def test_uniform_timestep_path_equals_the_per_sample_path(which, no_tf32):
+    """One timestep for the whole batch (what the reference's loops pass): the time-embedding path evaluated for ONE row and
+    broadcast by K5 gives the per-sample evaluation's result to fp32 round-off of five small matrix products."""
+    model, fused, x, _ = _pair(which)
+    t = torch.full((x.shape[0],), 0.372, device=DEV)
+    with torch.no_grad():
+        a = fused(x, t, return_dict=False)[0]
+        b = fused(x, t, return_dict=False, uniform_timestep=True)[0]
+        c = fused(x, 0.372).sample                                    # python scalar: uniform by construction
+        want = model(x, t, return_dict=False)[0]
+    scale = max(1.0, want.abs().max().item())
+    assert (a - b).abs().max().item() <= 1e-5 * scale and torch.equal(b, c)
+    assert (b - want).abs().max().item() <= 1e-5 * scale

@@ -36,7 +36,7 @@ def _np(t):
 
 def test_native_library_is_loaded():
     lib = _lib.load()
-    assert lib.bndm_version() == 1
+    assert lib.bndm_version() == 2
     with torch.cuda.device(DEV):
         assert lib.bndm_device_is_sm100() == 1, "tests expect a B200 (sm_100)"
     with open("/proc/self/maps") as f:
