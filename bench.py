@@ -422,7 +422,9 @@ def run_ours(args):
         # way (the stream is serial), so this adds no device idle time beyond one host round trip per T-launch step
         if sampler is not None:
             k2_ms.extend(sampler.step_kernel_ms())
+    torch.cuda.profiler.start()          # `ncu --profile-from-start off` lists exactly the launches of these steps
     ms_res, x_last = timed(step_resident, collect)
+    torch.cuda.profiler.stop()
     clock_info = clocks.stop()
     x_last = x_last.clone()
 

@@ -275,6 +275,28 @@ def test_contraction_kernel_is_tcgen05_and_tma_in_sass():
     assert "HMMA=" not in out.replace("UTCHMMA=", "")
 
 
+def test_streaming_contraction_is_tma_fed_packed_fma_in_sass():
+    """K1g (gemv_kernel): stage loads are one bulk copy (UBLKCP) + one tensor-map load (UTMALDG), the arithmetic is packed
+    fp32 FMA (FFMA2: 8 per column), no tensor-core instruction of any kind, and the cfg-1 instance does not spill more
+    than a few registers."""
+    import shutil
+    import subprocess
+    import sys
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "sass_evidence.py")],
+                         capture_output=True, text=True, check=True).stdout
+    blocks = {b.split("\n")[0]: b for b in out.split("\n\n") if b.startswith("bndm::gemv_kernel")}
+    assert len(blocks) == 4
+    for nc in (4, 8, 12, 16):
+        b = blocks[f"bndm::gemv_kernel<(int){nc}>"]
+        assert "UBLKCP=" in b and "UTMALDG=" in b and f"FFMA2={8 * nc}" in b, b
+        assert "UTCHMMA" not in b and "HMMA" not in b, b
+    assert "STACK:16 " in blocks["bndm::gemv_kernel<(int)12>"] or "STACK:0 " in blocks["bndm::gemv_kernel<(int)12>"]
+
+
 def test_c_abi_rejects_bad_arguments_before_touching_the_device():
     """Argument validation of the C ABI (include/bndm_b200.h "Errors"): bad calls return a negative code and a
     message through bndm_last_error() without launching anything, so this runs without a GPU.  The UNSUPPORTED
