@@ -185,6 +185,35 @@ class GraphedStep:
                 events[1].record()
 
 
+class GraphedLoop:
+    """The WHOLE sampling run -- T x [d = model(x, t_vec); K2(x, d)] -- captured as one CUDA graph: one replay per run,
+    no host work at all between the first UNet launch and the last update.  Possible because K2 keeps the
+    step index on the device and publishes the next timestep itself.  Capture costs T eager forwards once per
+    (model, shape, schedule); the graph's private pool is reused across the T iterations, so memory is one forward's."""
+
+    def __init__(self, model_call, stepper: "IadbStepper", x_static: torch.Tensor, n_steps: int, warmup: int = 2):
+        self.stepper, self.x, self.n_steps = stepper, x_static, n_steps
+        self.graph = torch.cuda.CUDAGraph()
+        dev = x_static.device
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        keep = x_static.clone()
+        with torch.cuda.stream(side):
+            for _ in range(min(warmup, n_steps)):         # lazy inits (cuDNN plans, workspaces) outside capture
+                stepper.step_(x_static, model_call(x_static, stepper.t_vec))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        x_static.copy_(keep)
+        stepper.reset()
+        with torch.cuda.graph(self.graph, stream=side):
+            for _ in range(n_steps):
+                stepper.step_(x_static, model_call(x_static, stepper.t_vec))
+        stepper.reset()
+
+    def replay(self):
+        self.stepper.note_step(self.n_steps)
+        self.graph.replay()
+
+
 class GraphedModel:
     """``model(x, t)`` for one fixed input shape replayed from a CUDA graph (north_star: "the UNet2DModel forward ...
     wrapped with CUDA Graphs per fixed shape").  Keeps the diffusers call conventions -- ``(x, t).sample`` and
@@ -237,7 +266,8 @@ class IadbSampler:
     captured [UNet -> K2] graph all persist across calls.  ``sample_iadb(..., use_graph=True)``
     keeps one of these per (model, shape, schedule).
 
-    graph: None (eager), 'step' (UNet+K2 in one graph) or 'unet' (UNet graph + eager K2).
+    graph: None (eager), 'step' (UNet+K2 in one graph, replayed T times), 'unet' (UNet graph + eager K2) or 'loop' (all T
+    steps in ONE graph, one replay per run; no per-step callback).
     time_step_kernel: record a CUDA event pair around every K2 launch (graph must not be 'step');
     ``step_kernel_ms()`` then returns the per-launch durations of the last run."""
 
@@ -283,7 +313,13 @@ class IadbSampler:
         if time_step_kernel and graph == "step":
             raise ValueError("time_step_kernel needs graph in (None, 'unet')")
         self.graphed = None
-        if graph is not None:
+        self.looped = None
+        if graph == "loop":
+            if time_step_kernel:
+                raise ValueError("time_step_kernel needs graph in (None, 'unet')")
+            with torch.no_grad():
+                self.looped = GraphedLoop(call, self.stepper, self.x, nb_step)
+        elif graph is not None:
             with torch.no_grad():
                 self.graphed = GraphedStep(call, self.stepper, self.x, fused=(graph == "step"))
         self.events = None
@@ -302,6 +338,11 @@ class IadbSampler:
                 raise ValueError("this sampler was built without conditioning")
             self.x_c.copy_(x_c)
         self.stepper.reset()
+        if self.looped is not None:
+            if on_step is not None:
+                raise ValueError("graph='loop' replays the whole run at once: no per-step callback (use graph='step')")
+            self.looped.replay()
+            return self.x
         for i, t in enumerate(reversed(range(self.nb_step))):
             ev = self.events[i] if self.events is not None else None
             if self.graphed is not None:
@@ -336,13 +377,15 @@ def _run_iadb(model, x0, x_c, nb_step, scheduler_alpha, scheduler_gamma, schedul
     x0 = _lib.require_cuda_f32(x0, "x0")
     params = tuple(float(p) for p in scheduler_params)
     key = (id(model), tuple(x0.shape), str(x0.device), nb_step, scheduler_alpha, scheduler_gamma, params, out_channel,
-           noise_type, float(alpha_param), None if x_c is None else tuple(x_c.shape), str(schedule_device), schedule_nb_steps)
+           noise_type, float(alpha_param), None if x_c is None else tuple(x_c.shape), str(schedule_device), schedule_nb_steps,
+           "loop" if use_graph == "loop" else "step")
     sampler = _sampler_cache.get(key) if use_graph else None
     if sampler is not None and sampler._model_ref() is not model:      # id() reuse after garbage collection
         sampler = None
     if sampler is None:
         sampler = IadbSampler(model, x0.shape, nb_step, scheduler_gamma, params, out_channel, noise_type,
-                              scheduler_alpha, alpha_param, x_c, x0.device, graph="step" if use_graph else None,
+                              scheduler_alpha, alpha_param, x_c, x0.device,
+                              graph=("loop" if use_graph == "loop" else "step") if use_graph else None,
                               schedule_device=schedule_device, schedule_nb_steps=schedule_nb_steps)
         if use_graph:
             if len(_sampler_cache) >= 4:
@@ -350,6 +393,10 @@ def _run_iadb(model, x0, x_c, nb_step, scheduler_alpha, scheduler_gamma, schedul
             _sampler_cache[key] = sampler
     if nb_step == 1000:
         log_freq = 100
+    if use_graph == "loop":
+        if train_or_test == "test":
+            raise ValueError("use_graph='loop' has no per-step snapshots: train_or_test must not be 'test'")
+        return sampler.run(x0, x_c=x_c).clone(), [], []
 
     x_all, per_step = [], []
     tic = [time.time()]
@@ -366,6 +413,8 @@ def _run_iadb(model, x0, x_c, nb_step, scheduler_alpha, scheduler_gamma, schedul
 def sample_iadb(model, x0, nb_step, *args, use_graph=False, schedule_device="cpu", **kwargs):
     """Both reference signatures (see module docstring).  Test mode returns
     ``(x, x_all, mean_step_seconds)`` like iadb_bn.py:376-378, otherwise ``x``.
+    ``use_graph``: False (eager), True (one captured [UNet -> K2] step replayed T times) or 'loop' (the whole T-step run
+    as ONE graph replay; not in test mode, which snapshots x between steps).
     ``schedule_device``: where alpha / gamma are evaluated ('cpu' = the reference's CPU path, the default; pass
     ``x0.device`` to reproduce a reference that runs its schedule kernels on the GPU, see schedules.iadb_table)."""
     if len(args) + len(kwargs) == 1:                  # iadb_bn.py:287 -- (scheduler_params,) + module `opt`

@@ -171,3 +171,60 @@ def test_one_handle_on_two_streams_is_serialised(L_dev, L_np):
     g.replay()
     torch.cuda.synchronize()
     np.testing.assert_allclose(captured.cpu().numpy(), want[0], rtol=RTOL, atol=ATOL)
+
+
+# ------------------------------------------------------------------ N1: whole-loop graph, checkpoint files
+def test_whole_loop_graph_equals_per_step_graph():
+    """All T steps captured as ONE CUDA graph (K2 keeps the step index on the device) == T replays of the one-step graph
+    == the eager loop, bit for bit; the second run replays the same graph with a new x0."""
+    from bndm_b200.fused_unet import fuse_unet
+    from bndm_b200.unet import get_latent_model
+    torch.manual_seed(0)
+    model = fuse_unet(get_latent_model(256, 8).to(DEV).eval())
+    for seed in (1, 2):
+        x0 = torch.randn(2, 4, 32, 32, generator=torch.Generator().manual_seed(seed)).to(DEV)
+        args = (7, "sigmoid", (0.2, 0.0, 3.0), 8, "gaussianBN", "train")
+        eager = bb.sample_iadb(model, x0, *args)
+        step = bb.sample_iadb(model, x0, *args, use_graph=True)
+        loop = bb.sample_iadb(model, x0, *args, use_graph="loop")
+        assert torch.equal(eager, step) and torch.equal(step, loop)
+    with pytest.raises(ValueError):
+        bb.sample_iadb(model, x0, 7, "sigmoid", (0.2, 0.0, 3.0), 8, "gaussianBN", "test", use_graph="loop")
+
+
+def test_checkpoint_files_with_diffusers_key_names_load(tmp_path):
+    """iadb_bn.py:714 `model.load_state_dict(torch.load(model.ckpt))` and ddim_diffusers.py:642 `from_pretrained` (a
+    safetensors file): a state dict under the diffusers parameter names round-trips through both file formats into a
+    fresh model, and the fused evaluator built from the loaded model reproduces the original's output."""
+    from bndm_b200.fused_unet import fuse_unet
+    from bndm_b200.unet import get_latent_model
+    torch.manual_seed(3)
+    src = get_latent_model(256, 8).to(DEV).eval()
+    sd = {k: v.detach().cpu() for k, v in src.state_dict().items()}
+    for needle in ("conv_in.weight", "time_embedding.linear_1.weight", "down_blocks.0.resnets.0.norm1.weight",
+                   "down_blocks.0.resnets.0.time_emb_proj.bias", "down_blocks.0.downsamplers.0.conv.weight",
+                   "mid_block.attentions.0.to_q.weight", "mid_block.attentions.0.to_out.0.bias",
+                   "up_blocks.0.resnets.0.conv_shortcut.weight", "up_blocks.0.upsamplers.0.conv.weight",
+                   "conv_norm_out.weight", "conv_out.bias"):
+        assert needle in sd, needle
+    x = torch.randn(2, 4, 32, 32, device=DEV)
+    t = torch.tensor([0.8, 0.3], device=DEV)
+    with torch.no_grad():
+        want = src(x, t, return_dict=False)[0]
+    torch.save(sd, tmp_path / "model.ckpt")
+    files = {"ckpt": lambda: torch.load(tmp_path / "model.ckpt", map_location="cpu")}
+    try:
+        from safetensors.torch import load_file, save_file
+        save_file(sd, str(tmp_path / "diffusion_pytorch_model.safetensors"))
+        files["safetensors"] = lambda: load_file(str(tmp_path / "diffusion_pytorch_model.safetensors"))
+    except ImportError:
+        pass
+    for name, load in files.items():
+        torch.manual_seed(99)                                   # a differently initialised model ...
+        fresh = get_latent_model(256, 8).to(DEV).eval()
+        missing, unexpected = fresh.load_state_dict(load(), strict=True)      # ... takes every key, none left over
+        assert not missing and not unexpected, name
+        with torch.no_grad():
+            assert torch.equal(fresh(x, t, return_dict=False)[0], want), name
+            got = fuse_unet(fresh)(x, t, return_dict=False)[0]
+        assert (got - want).abs().max().item() <= 5e-3 * max(1.0, want.abs().max().item()), name
