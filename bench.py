@@ -487,7 +487,7 @@ def run_ours(args):
     unet_tflops = flops_per_image * B * T / ((ms_res / args.steps) * 1e-3) / 1e12
     kpf = getattr(model, "kernels_per_forward", 0) or 0
     noise_calls = T if kind == "ddim" else 1
-    noise_launches = (1 if n_cols <= 12 else 3) + (1 if (RES != 64) else 0)
+    noise_launches = (1 if n_cols <= 16 else 3) + (1 if (RES != 64) else 0)
 
     line = {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -501,7 +501,7 @@ def run_ours(args):
                            + "; pinned host in/out"},
             "gpu_launches": args.steps * (noise_calls * noise_launches + T * (1 + kpf)),
             "gpu_launches_note": f"per step: {noise_calls} x get_noise_v2 ({noise_launches} launches: "
-                                 f"{'K1g' if n_cols <= 12 else 'K1a pack + K1b contraction + K1c combine'}) + {T} x (update kernel + "
+                                 f"{'K1g' if n_cols <= 16 else 'K1a pack + K1b contraction + K1c combine'}) + {T} x (update kernel + "
                                  f"{kpf} K5/K6/K7/K8 launches inside the UNet forward); cuDNN/cuBLAS/ATen kernels are not counted",
             "clocks": clock_info,
             "checksum": checksum,
@@ -620,7 +620,7 @@ def roofline_get_noise(micro, pk, this_shape):
     res, B, C = this_shape
     n_cols = B * C * (4 if res == 128 else 1)
     out = {"cfg1": entry((64, 4, 3), "gemv_kernel<12> (K1g: TMA-streamed fp32 FFMA2 contraction, complete rows per CTA, one launch)"),
-           "this_config": entry(this_shape, "gemv_kernel (K1g)" if n_cols <= 12 else
+           "this_config": entry(this_shape, "gemv_kernel (K1g)" if n_cols <= 16 else
                                 "gemm_tc_kernel (K1b: triangular L.z contraction, tcgen05 3xTF32) + K1a pack + K1c combine")}
     out["cfg1"]["traffic"] = ncu_traffic("gemv_kernel<12> B=4")
     out["this_config"]["traffic"] = ncu_traffic("gemm_tc_kernel<96,0,1> B=64") if this_shape == (64, 64, 3) else None

@@ -73,6 +73,7 @@ struct bndm_L {
   // optional per-launch timing (bndm_profile_enable)
   int *gv_sched[4] = {nullptr, nullptr, nullptr, nullptr};   // owned: K1g row schedules [2 res32 + dense] -> [n_sms][kGemvTableStride]
   float *gv_L[4] = {nullptr, nullptr, nullptr, nullptr};     // owned: L in the stream order of that schedule
+  GvTable *gv_tab[4] = {nullptr, nullptr, nullptr, nullptr}; // owned (host): the schedule as kernel parameters
   int gv_variant = 0;
   int n_sms = 148;
   unsigned long long *trace = nullptr;   // debug: per-CTA time stamps of the contraction kernel (caller-owned)
@@ -180,10 +181,13 @@ static int gv_build(bndm_L *h, int k, cudaStream_t s) {
   if (e == cudaSuccess) e = cudaMemcpyAsync(sched, host, n * sizeof(int), cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = launch_gemv_pack_L(h->L, Lg, sched, h->n_sms, h->gv_variant, k & 1, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  GvTable *tab = e == cudaSuccess ? gemv_make_table(host, h->n_sms, k & 1) : nullptr;
   delete[] host;
   if (e != cudaSuccess) { cudaFree(sched); cudaFree(Lg); return fail_cuda(e, "K1g schedule / stream-ordered L"); }
+  if (!tab) { cudaFree(sched); cudaFree(Lg); return BNDM_OK; }     // more SMs than the parameter block holds: K1b takes over
   h->gv_sched[k] = sched;
   h->gv_L[k] = Lg;
+  h->gv_tab[k] = tab;
   return BNDM_OK;
 }
 
@@ -317,7 +321,7 @@ int bndm_free_L(bndm_L *h) {
   cudaFree(h->Lt_dense);
   cudaFree(h->Lr);
   cudaFree(h->tile_counters);
-  for (int k = 0; k < 4; ++k) { cudaFree(h->gv_sched[k]); cudaFree(h->gv_L[k]); }
+  for (int k = 0; k < 4; ++k) { cudaFree(h->gv_sched[k]); cudaFree(h->gv_L[k]); gemv_free_table(h->gv_tab[k]); }
   delete h;
   return BNDM_OK;
 }
@@ -416,7 +420,7 @@ static int get_noise_impl(bndm_L *h, const float *z, const float *gamma, float *
     GemvArgs g;
     g.Lg = h->gv_L[gv_table];
     g.z_cols = gather ? h->z_raw : z;
-    g.sched = h->gv_sched[gv_table];
+    g.table = h->gv_tab[gv_table];
     g.n_ctas = h->n_sms;
     g.dense = dense;
     g.variant = h->gv_variant;

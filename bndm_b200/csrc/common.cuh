@@ -208,13 +208,16 @@ void tc_set_policy(int fused, int raw);   // policy: combine fused into the cont
 // ---- K1g: streaming fp32 contraction for <= kGemvMaxCols columns (noise_gemv.cu) -------------
 constexpr int kGemvSlots = 8;      // quads (4 consecutive rows of L) a CTA may own
 constexpr int kGemvMaxCols = 16;
-constexpr int kGemvAutoCols = 12;  // the default rule picks K1g up to here (the 16-column instance spills: K1b is as fast there)
+constexpr int kGemvAutoCols = 16;  // the default rule picks K1g up to here (measured: 18.4 us at 16 columns, K1b 19.8)
 constexpr int kGemvTraceStride = 128;   // u64 per CTA of K1g's debug trace: [0..3] summary, [8+c] stage c requested, [48+c] landed, [88+c] released
 constexpr int kGemvTableStride = 10;   // ints per CTA in the schedule table: 8 slots, first stream block, load
+struct GvTable;            // a schedule in its kernel-parameter form (noise_gemv.cu)
+GvTable *gemv_make_table(const int *sched_host, int n_ctas, int dense);     // null if the device has too many SMs for the parameter block
+void gemv_free_table(GvTable *t);
 struct GemvArgs {
   const float *Lg;         // L in K1g's stream order (launch_gemv_pack_L)
   const float *z_cols;     // white columns [n_cols][4096]
-  const int *sched;        // device, [n_ctas][kGemvTableStride] (gemv_build_schedule)
+  const GvTable *table;    // host, the schedule of this row set (gemv_make_table)
   int n_ctas;
   int dense;               // L is not lower-triangular (or the caller forces the dense walk)
   int variant;             // gemv_variant()

@@ -51,7 +51,7 @@ enum {
                                  res 32 is tiled 2x2 (:78-79), res 128 is cut in quadrants
                                  concatenated on dim 0 (:131-132)                              */
 /* Which contraction kernel:                                                                 */
-#define BNDM_GEMM_AUTO    0u  /* default: K1g for <= 12 GEMM columns (HBM-bound GEMV regime),
+#define BNDM_GEMM_AUTO    0u  /* default: K1g for <= 16 GEMM columns (HBM-bound GEMV regime),
                                  K1b (tcgen05) above                                          */
 #define BNDM_GEMM_SIMT    16u /* fp32 FFMA split-K witness kernel (same results to ~1e-6)     */
 #define BNDM_FORCE_DENSE  32u /* ignore the triangular structure of L (testing)               */

