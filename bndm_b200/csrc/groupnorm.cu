@@ -415,7 +415,7 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
   if (!res && !sum_out) {
     // cluster path: P CTAs per (sample, channel block), slab of HW / P pixels in shared memory
     const size_t row_bytes = (size_t)cblk * 4;
-    static int slab_kb = 0;      // BNDM_GN_SLAB_KB: target slab size per CTA (experiments); default 64
+    static thread_local int slab_kb = 0;      // BNDM_GN_SLAB_KB: target slab size per CTA (experiments); default 64
     if (!slab_kb) {
       const char *e = getenv("BNDM_GN_SLAB_KB");
       slab_kb = e ? atoi(e) : 64;
@@ -462,9 +462,11 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
       cfg.attrs = attr;
       cfg.numAttrs = 1;
       // persistent grid: as many clusters as can be resident at once (cached per launch shape)
-      static int cache_key[3] = {0, 0, 0}, cache_val = 0;
+      static thread_local int cache_key[4] = {0, 0, 0, -1}, cache_val = 0;     // per host thread (and device): no shared mutable state
       int max_clusters = 0;
-      if (cache_key[0] == P && cache_key[1] == nt && cache_key[2] == (int)smem) {
+      int dev_id = 0;
+      cudaGetDevice(&dev_id);
+      if (cache_key[0] == P && cache_key[1] == nt && cache_key[2] == (int)smem && cache_key[3] == dev_id) {
         max_clusters = cache_val;
       } else {
         cfg.gridDim = dim3((unsigned)P, 1, 1);
@@ -472,9 +474,23 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
           cudaGetLastError();
           max_clusters = 148 / P > 0 ? 148 / P : 1;
         }
-        cache_key[0] = P; cache_key[1] = nt; cache_key[2] = (int)smem; cache_val = max_clusters;
+        cache_key[0] = P; cache_key[1] = nt; cache_key[2] = (int)smem; cache_key[3] = dev_id; cache_val = max_clusters;
       }
-      const int n_clusters = n_items < max_clusters ? n_items : max_clusters;
+      int n_clusters = n_items < max_clusters ? n_items : max_clusters;
+      {
+        // Even rounds: a persistent cluster walks ceil(n_items / n_clusters) items, so 256 items on 48 clusters cost 6
+        // rounds with a sixth of the machine idle in the last one.  Take the FEWEST clusters that still finish in the
+        // same number of rounds (fewer clusters = fewer cluster barriers in flight, same span) -- or, when
+        // BNDM_GN_EVEN=2, the largest count that divides the items evenly if that loses no more than a quarter of the
+        // resident clusters.
+        static thread_local int even_mode = -1;
+        if (even_mode < 0) { const char *e = getenv("BNDM_GN_EVEN"); even_mode = e ? atoi(e) : 0; }
+        const int rounds = (n_items + n_clusters - 1) / n_clusters;
+        if (even_mode == 1) n_clusters = (n_items + rounds - 1) / rounds;
+        if (even_mode == 2)
+          for (int c = n_clusters; c >= (3 * n_clusters) / 4 && c >= 1; --c)
+            if (n_items % c == 0) { n_clusters = c; break; }
+      }
       cfg.gridDim = dim3((unsigned)(P * n_clusters), 1, 1);
       return cudaLaunchKernelEx(&cfg, groupnorm_nhwc_cluster_kernel<true>, a, P, ppc, n_items);
     }

@@ -45,6 +45,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "out_map.cuh"
 #include "ptx.cuh"
@@ -533,18 +535,20 @@ int tc_pick_nb(int n_cols) {
 }
 
 int tc_num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
-      n = 148;
-  }
+  // per device (a process may drive several GPUs from several threads): a small table indexed by the current device
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+  if (dev >= 0 && dev < 64) cache[dev] = n;      // benign race: every writer stores the same value
   return n;
 }
 
 // Policy knobs: -1 = default rule, 0 = off, 1 = on.  Initialised from BNDM_TC_FUSED / BNDM_TC_RAWL,
 // overridable at run time through bndm_debug_set_policy (tests sweep every variant).
-static int g_policy_fused = -2, g_policy_raw = -2;
+static std::atomic<int> g_policy_fused{-2}, g_policy_raw{-2};     // test hooks: process-wide, but race-free
 static int env_policy(const char *name) {
   const char *e = getenv(name);
   return e ? (e[0] == '1' ? 1 : 0) : -1;

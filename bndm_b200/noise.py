@@ -69,21 +69,30 @@ class CovMatL:
         self._finalizer()
 
 
-_handles: "dict[tuple, CovMatL]" = {}
+_handles: "dict[tuple, tuple]" = {}      # (data_ptr, device, shape) -> (_version, handle); insertion order = age
+_MAX_HANDLES = 4
 
 
 def prepare_L(cov_mat_L, max_columns: int = 192) -> CovMatL:
-    """Returns the cached handle for this tensor (keyed on storage pointer + device)."""
+    """Returns the cached handle for this matrix.  A cached handle keeps the caller's tensor object alive (``_orig``,
+    next to the contiguous fp32 tensor the kernels read), so the memory a key points at cannot be freed and handed
+    to another tensor while the entry exists: a new L at a recycled address can never inherit stale operand copies.
+    In-place modification (the tensor's ``_version``) drops the entry; at most 4 matrices are kept."""
     if isinstance(cov_mat_L, CovMatL):
         return cov_mat_L
     if not isinstance(cov_mat_L, torch.Tensor):
         raise TypeError("cov_mat_L must be a torch.Tensor or CovMatL")
-    key = (cov_mat_L.data_ptr(), str(cov_mat_L.device), tuple(cov_mat_L.shape), cov_mat_L._version)
-    h = _handles.get(key)
-    if h is None:
-        for k in [k for k in _handles if k[:2] == key[:2]]:      # same buffer, stale contents
-            _handles.pop(k).close()
-        h = _handles[key] = CovMatL(cov_mat_L, max_columns)
+    key = (cov_mat_L.data_ptr(), str(cov_mat_L.device), tuple(cov_mat_L.shape), tuple(cov_mat_L.stride()))
+    hit = _handles.get(key)
+    if hit is not None:
+        if hit[0] == cov_mat_L._version:
+            return hit[1]
+        _handles.pop(key)[1].close()                              # modified in place since the copies were made
+    while len(_handles) >= _MAX_HANDLES:
+        _handles.pop(next(iter(_handles)))[1].close()
+    h = CovMatL(cov_mat_L, max_columns)
+    h._orig = cov_mat_L                                           # pins the keyed memory for the lifetime of the entry
+    _handles[key] = (cov_mat_L._version, h)
     return h
 
 

@@ -228,3 +228,60 @@ def test_checkpoint_files_with_diffusers_key_names_load(tmp_path):
             assert torch.equal(fresh(x, t, return_dict=False)[0], want), name
             got = fuse_unet(fresh)(x, t, return_dict=False)[0]
         assert (got - want).abs().max().item() <= 5e-3 * max(1.0, want.abs().max().item()), name
+
+
+def test_prepare_L_cache_is_tied_to_live_memory(L_np):
+    """The handle cache can never serve stale operand copies: an entry pins its tensor, in-place edits drop it, and a
+    different matrix -- even one that would have been allocated at a recycled address -- gets its own handle."""
+    from bndm_b200 import noise as bn
+    from oracle import noise as on
+    x = torch.randn(2, 3, 64, 64, device=DEV)
+    La = torch.from_numpy(L_np).to(DEV)
+    ha = bb.prepare_L(La)
+    assert bb.prepare_L(La) is ha
+    ptr = La.data_ptr()
+    del La                                             # the caller drops its tensor: the cache entry keeps the memory pinned
+    torch.cuda.empty_cache()
+    Lb = torch.from_numpy(np.ascontiguousarray(np.tril(L_np.T * 0.5 + L_np))).to(DEV)       # another matrix
+    assert Lb.data_ptr() != ptr
+    hb = bb.prepare_L(Lb)
+    assert hb is not ha
+    want = on.get_noise_np(x.cpu().numpy(), Lb.cpu().numpy(), None, "GBN", "train", True)[1]
+    np.testing.assert_allclose(bb.get_noise_v2(DEV, x, Lb, None, None, "GBN", "train", True)[1].cpu().numpy(), want, rtol=RTOL, atol=ATOL)
+    Lb.mul_(2.0)                                       # in-place edit: the cached copies are stale, a new handle is built
+    hc = bb.prepare_L(Lb)
+    assert hc is not hb
+    np.testing.assert_allclose(bb.get_noise_v2(DEV, x, Lb, None, None, "GBN", "train", True)[1].cpu().numpy(), 2 * want, rtol=RTOL, atol=ATOL)
+    assert len(bn._handles) <= bn._MAX_HANDLES
+
+
+@pytest.mark.parametrize("sub,bs", [("1", 4), ("2", 8)])
+def test_env_selected_contraction_instances(sub, bs, tmp_path):
+    """The k-stages-per-pipeline-stage knob BNDM_TC_SUB reaches two instances the default rule never picks
+    (gemm_tc_kernel<16,true,1> and <32,true,2>); it is read once per process, so each runs in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+    code = f"""
+import numpy as np, torch, sys
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+import bndm_b200 as bb
+from bndm_b200.synth import hashed_tril
+from oracle import noise as on
+dev = torch.device('cuda:0')
+L_np = hashed_tril(seed=0)
+L = torch.from_numpy(L_np).to(dev)
+rng = np.random.default_rng(5)
+x = rng.standard_normal(({bs}, 3, 64, 64)).astype(np.float32)
+g = rng.random({bs}).astype(np.float32)
+want = on.get_noise_np(x, L_np, g, 'gaussianBN', 'train', True)
+got = bb.get_noise_v2(dev, torch.from_numpy(x).to(dev), L, torch.from_numpy(g).to(dev), None, 'gaussianBN', 'train', True, gemm='tc')
+again = bb.get_noise_v2(dev, torch.from_numpy(x).to(dev), L, torch.from_numpy(g).to(dev), None, 'gaussianBN', 'train', True, gemm='tc')
+for a, b, w in zip(got, again, want):
+    assert torch.equal(a, b)
+    np.testing.assert_allclose(a.cpu().numpy(), w, rtol=1e-4, atol=1e-5)
+print('ok')
+"""
+    env = dict(os.environ, BNDM_TC_SUB=sub, BNDM_TC_RAWL="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "ok" in out.stdout, (out.stdout + out.stderr)[-2000:]
