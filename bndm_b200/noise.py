@@ -87,9 +87,10 @@ def prepare_L(cov_mat_L, max_columns: int = 192) -> CovMatL:
     if hit is not None:
         if hit[0] == cov_mat_L._version:
             return hit[1]
-        _handles.pop(key)[1].close()                              # modified in place since the copies were made
+        _handles.pop(key)                                         # modified in place since the copies were made
     while len(_handles) >= _MAX_HANDLES:
-        _handles.pop(next(iter(_handles)))[1].close()
+        _handles.pop(next(iter(_handles)))                        # dropped, not closed: a caller may still hold the
+                                                                  # handle; its finalizer frees it with the last reference
     h = CovMatL(cov_mat_L, max_columns)
     h._orig = cov_mat_L                                           # pins the keyed memory for the lifetime of the entry
     _handles[key] = (cov_mat_L._version, h)

@@ -161,6 +161,7 @@ class GraphedStep:
         keep = x_static.clone()
         with torch.cuda.stream(side):
             for _ in range(warmup):                       # lazy inits (cuDNN plans, workspaces) outside capture
+                stepper.reset()                           # (a 1-step schedule must not count the warm-ups as its run)
                 stepper.step_(x_static, model_call(x_static, stepper.t_vec))
         torch.cuda.current_stream(dev).wait_stream(side)
         x_static.copy_(keep)
@@ -199,7 +200,8 @@ class GraphedLoop:
         side.wait_stream(torch.cuda.current_stream(dev))
         keep = x_static.clone()
         with torch.cuda.stream(side):
-            for _ in range(min(warmup, n_steps)):         # lazy inits (cuDNN plans, workspaces) outside capture
+            for _ in range(warmup):                       # lazy inits (cuDNN plans, workspaces) outside capture
+                stepper.reset()
                 stepper.step_(x_static, model_call(x_static, stepper.t_vec))
         torch.cuda.current_stream(dev).wait_stream(side)
         x_static.copy_(keep)
