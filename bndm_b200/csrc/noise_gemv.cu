@@ -115,6 +115,20 @@ __device__ __forceinline__ void fma2(float2 &d, const float2 a, const float2 b) 
   d = reinterpret_cast<float2 &>(dd);
 }
 
+// Ring slot and mbarrier phase of stage c.  Even stages live in the even slots, odd stages in the odd ones: a consumer
+// warp only ever waits for the stages of ITS parity, and a parity wait is only meaningful for a waiter that sees every
+// use of the barrier (a warp that skipped one use would take the completion of the use before for the one it waits
+// for -- with a plain c % stages ring and an odd depth that happened, rarely, and ended in a trap).  Returns true for
+// the first use of the slot.
+__device__ __forceinline__ bool gv_ring_slot(int c, int stages, int &slot, uint32_t &phase) {
+  const int par = c & 1, k = c >> 1;
+  const int n = par ? stages / 2 : (stages + 1) / 2;       // slots of this parity
+  const int u = k / n;
+  slot = 2 * (k - u * n) + par;
+  phase = (uint32_t)u & 1u;
+  return u == 0;
+}
+
 // one k-chunk of one consumer warp: its quad x NC columns x (this lane's 4 k)
 template <int NC>
 __device__ __forceinline__ void gv_chunk(const uint8_t *lp, const uint8_t *zp, float2 (&acc)[2][NC]) {
@@ -197,9 +211,10 @@ gemv_kernel(const GemvKernelArgs a, const __grid_constant__ CUtensorMap map_z, c
 #pragma unroll
       for (int q = 0; q < kGemvSlots; ++q) nact += (kend[q] > ca * kGvKW ? 1 : 0) + ((cb > ca && kend[q] > cb * kGvKW) ? 1 : 0);
       if ((c % kGvProducers) == pw) {
-        const int st = c % a.stages;
-        const uint32_t ph = (uint32_t)(c / a.stages) & 1u;
-        if (c >= a.stages) mbar_wait(&empty_bar[st], ph ^ 1u);       // the first round finds every slot free
+        int st;
+        uint32_t ph;
+        const bool first_use = gv_ring_slot(c, a.stages, st, ph);
+        if (!first_use) mbar_wait(&empty_bar[st], ph ^ 1u);          // the first use of a slot finds it free
         const uint32_t sa = smem_u32(base + (size_t)st * a.stage_bytes);
         if (elect_one()) {
           mbar_expect_tx(&full_bar[st], (uint32_t)nact * kGvQuadBytes + (cb > ca ? 2u : 1u) * Cfg::kZBytes);
@@ -251,8 +266,9 @@ gemv_kernel(const GemvKernelArgs a, const __grid_constant__ CUtensorMap map_z, c
     const uint32_t l_off = (uint32_t)slot * kGvQuadBytes + (uint32_t)lane * 16u;
     const uint32_t z_off = a.zoff + (uint32_t)lane * 16u;
     for (int c = par; c < nst; c += 2) {
-      const int st = c % a.stages;
-      const uint32_t ph = (uint32_t)(c / a.stages) & 1u;
+      int st;
+      uint32_t ph;
+      gv_ring_slot(c, a.stages, st, ph);
       const int ca = c, cb = n_chunks - 1 - c;
       int nact_a = 0;                                   // chunk b's blocks sit behind chunk a's active ones
 #pragma unroll
