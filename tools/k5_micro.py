@@ -30,8 +30,8 @@ for C, H in shapes:
         ts.append(e0.elapsed_time(e1) * 1e3 / 20)
     us = statistics.median(ts)
     nbytes = 2 * B * C * H * H * 4
-    tt = []
-    for _ in range(5):
+    tt = [float("nan")]
+    for _ in range(0 if os.environ.get("K5_NO_TORCH") else 5):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(20):
