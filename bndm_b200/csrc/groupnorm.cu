@@ -128,9 +128,24 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_kernel(GnArgs a)
   if (a.add_bc) add = __ldg(reinterpret_cast<const float4 *>(a.add_bc + (size_t)b * a.add_stride + c));
 
   // ---- pass 1: s = x (+ res) (+ add), shifted sums -------------------------------------------
+  // shifted sums over at most 64 pixels at a time, folded into running moments (Chan): a thread walks up to
+  // thousands of pixels at 128^2 / 256^2 and one long fp32 sum would lose ~sqrt(n) ulps
   float shift = 0.f, sum = 0.f, sq = 0.f, cnt = 0.f;
   bool first = true;
+  Moments run = {0.f, 0.f, 0.f};
+  int in_chunk = 0;
   for (int p = prow; p < a.HW; p += pstride * 4) {
+    if (in_chunk == 16) {
+      Moments c;
+      c.n = cnt;
+      c.mean = shift + sum / cnt;
+      c.m2 = fmaxf(sq - sum * sum / cnt, 0.f);
+      run = merge(run, c);
+      sum = sq = cnt = 0.f;
+      first = true;
+      in_chunk = 0;
+    }
+    ++in_chunk;
     float4 v[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -162,6 +177,7 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_kernel(GnArgs a)
   m.n = cnt;
   m.mean = cnt > 0.f ? shift + sum / cnt : 0.f;
   m.m2 = cnt > 0.f ? fmaxf(sq - sum * sum / cnt, 0.f) : 0.f;
+  m = merge(run, m);
   s_part[tid] = m;
   __shared__ Moments s_grp[32];
   block_group_moments(s_part, s_grp, tid, blockDim.x, q, a.cpg >> 2, n_groups);
@@ -411,16 +427,31 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
   const int q = cblk / 4;
   if (q > kGnMaxThreads || cblk / a.cpg > 32) return cudaErrorInvalidValue;
   const int threads = kGnMaxThreads / q * q;
+  const int cblk0 = cblk;                          // the register kernel below keeps whole 128-byte lines
 
   if (!res && !sum_out) {
     // cluster path: P CTAs per (sample, channel block), slab of HW / P pixels in shared memory
-    const size_t row_bytes = (size_t)cblk * 4;
     static thread_local int slab_kb = 0;      // BNDM_GN_SLAB_KB: target slab size per CTA (experiments); default 64
     if (!slab_kb) {
       const char *e = getenv("BNDM_GN_SLAB_KB");
       slab_kb = e ? atoi(e) : 64;
       if (slab_kb < 8 || slab_kb > 192) slab_kb = 64;
     }
+    // 128^2 activations: a (sample, 32-channel block) is 2 MiB -- 16 CTAs x 128 KiB, i.e. non-portable clusters on one
+    // CTA per SM (measured 2.2 TB/s).  Narrower channel blocks keep the item inside 8 x 64 KiB (three CTAs per SM):
+    // 64- / 32-byte row pieces instead of whole 128-byte lines, still whole groups: 3.4 TB/s at 128^2 x 128 / 256 channels.
+    static thread_local int force_cblk = -1;   // BNDM_GN_CBLK: force a channel block (experiments)
+    if (force_cblk < 0) { const char *e = getenv("BNDM_GN_CBLK"); force_cblk = e ? atoi(e) : 0; }
+    if (force_cblk > 0 && force_cblk % a.cpg == 0 && C % force_cblk == 0 && force_cblk % 4 == 0) {
+      cblk = force_cblk;
+    } else {
+      while ((size_t)HW * cblk * 4 > (size_t)8 * slab_kb * 1024 && cblk % 2 == 0 && (cblk / 2) % a.cpg == 0 && (cblk / 2) % 8 == 0 &&
+             (!x2 || C1 % (cblk / 2) == 0))
+        cblk /= 2;
+    }
+    a.cblk = cblk;
+    const int q = cblk / 4;
+    const size_t row_bytes = (size_t)cblk * 4;
     const int p_max = slab_kb < 64 ? 16 : 8;
     int P = 1;
     while (P < p_max && ((size_t)((HW + P - 1) / P) * row_bytes > (size_t)slab_kb * 1024)) P *= 2;
@@ -496,7 +527,8 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
     }
   }
   if (x2) return cudaErrorInvalidValue;                           // slab does not fit: caller concatenates first
-  dim3 grid(C / cblk, B);
+  a.cblk = cblk0;
+  dim3 grid(C / cblk0, B);
   groupnorm_nhwc_kernel<<<grid, threads, 0, s>>>(a);
   return cudaGetLastError();
 }

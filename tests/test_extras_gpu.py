@@ -122,7 +122,7 @@ def test_conditional_sampler_reuses_one_graph_for_new_conditioning():
         from oracle.toy import ToyCond
         model = ToyCond(6)
         x0 = torch.randn(2, 3, 16, 16, device=DEV)
-        n_before = len(bs._sampler_cache)
+        keys_before = set(bs._sampler_cache)
         outs, wants = [], []
         xc = torch.randn(2, 3, 16, 16, device=DEV)
         for i in range(3):
@@ -133,7 +133,7 @@ def test_conditional_sampler_reuses_one_graph_for_new_conditioning():
             outs.append(bb.sample_iadb_conditional(model, x0, xc, 5, (1000.0, 0.0, 3.0), use_graph=True))
             wants.append(osam.sample_iadb_conditional(model, x0, xc, 5, (1000.0, 0.0, 3.0), osam.make_opt(
                 noise_type="gaussianBN", out_channel=6, train_or_test="train", nb_steps=5)))
-        assert len(bs._sampler_cache) == n_before + 1             # one capture served all three
+        assert len(set(bs._sampler_cache) - keys_before) == 1      # one capture served all three (the cache holds at most 4)
         for g_, w_ in zip(outs, wants):
             np.testing.assert_allclose(g_.cpu().numpy(), w_.cpu().numpy(), rtol=RTOL, atol=ATOL)
     finally:

@@ -181,7 +181,7 @@ def test_full_size_unet_sampling_graph_equals_eager_short():
 
 # ------------------------------------------------------------------ K5: fused GroupNorm (+adds) + SiLU, NHWC
 @pytest.mark.parametrize("B,C,H", [(3, 128, 64), (2, 256, 16), (2, 384, 8), (1, 512, 4), (2, 1024, 2), (2, 768, 8), (5, 128, 32),
-                                   (2, 384, 64), (2, 256, 64), (1, 128, 128)])
+                                   (2, 384, 64), (2, 256, 64), (1, 128, 128), (2, 256, 128), (1, 128, 256)])
 @pytest.mark.parametrize("mode", ["plain", "add_bc", "res_sum", "nosilu"])
 def test_groupnorm_silu_nhwc_matches_torch(B, C, H, mode):
     from bndm_b200.fused_unet import groupnorm_silu_nhwc
@@ -215,7 +215,8 @@ def test_groupnorm_silu_nhwc_matches_torch(B, C, H, mode):
     assert torch.equal(y2, y), "fixed-order statistics must be bit-reproducible"
 
 
-@pytest.mark.parametrize("B,C1,C2,H", [(2, 128, 128, 64), (2, 256, 128, 32), (3, 512, 512, 4), (2, 512, 256, 8), (2, 128, 128, 16)])
+@pytest.mark.parametrize("B,C1,C2,H", [(2, 128, 128, 64), (2, 256, 128, 32), (3, 512, 512, 4), (2, 512, 256, 8), (2, 128, 128, 16),
+                                       (2, 128, 128, 128), (1, 256, 128, 128)])
 def test_groupnorm_two_sources_equals_cat(B, C1, C2, H):
     from bndm_b200.fused_unet import groupnorm_silu_nhwc
     a = torch.randn(B, C1, H, H, device=DEV).contiguous(memory_format=torch.channels_last)
