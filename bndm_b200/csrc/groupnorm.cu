@@ -437,17 +437,22 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
       slab_kb = e ? atoi(e) : 64;
       if (slab_kb < 8 || slab_kb > 192) slab_kb = 64;
     }
-    // 128^2 activations: a (sample, 32-channel block) is 2 MiB -- 16 CTAs x 128 KiB, i.e. non-portable clusters on one
-    // CTA per SM (measured 2.2 TB/s).  Narrower channel blocks keep the item inside 8 x 64 KiB (three CTAs per SM):
-    // 64- / 32-byte row pieces instead of whole 128-byte lines, still whole groups: 3.4 TB/s at 128^2 x 128 / 256 channels.
+    // Channel block of the cluster path.  Whole 128-byte lines (32 channels) make a 64^2 item 512 KiB = 8 CTAs x 64 KiB,
+    // and clusters of 8 fit on only 128 of the 148 SMs; at 128^2 the item is 2 MiB = 16 CTAs x 128 KiB, non-portable
+    // clusters on one CTA per SM (measured 2.2 TB/s).  Narrower blocks -- 64- or 32-byte row pieces, still whole groups --
+    // keep three 64 KiB CTAs per SM and let the clusters shrink: measured (B200, tools/k5_micro.py)
+    //   64^2 x 128 ch: 32 ch / P=8 3.96 TB/s, 16 ch / P=4 4.44, 8 ch / P=2 3.94;   128^2 x 128 ch: 32 ch 2.2, 16 ch 3.2, 8 ch / P=8 3.4.
+    // Rule: halve towards 4 x 64 KiB while the pieces stay >= 64 bytes, then towards 8 x 64 KiB down to 32-byte pieces.
     static thread_local int force_cblk = -1;   // BNDM_GN_CBLK: force a channel block (experiments)
     if (force_cblk < 0) { const char *e = getenv("BNDM_GN_CBLK"); force_cblk = e ? atoi(e) : 0; }
+    // (the same block with or without a second source -- a thread picks its source by its own channel quad -- so
+    // the two-source call stays bit-identical to the call on the concatenated tensor)
+    auto can_halve = [&](int cb) { return cb % 2 == 0 && (cb / 2) % a.cpg == 0 && (cb / 2) % 8 == 0; };
     if (force_cblk > 0 && force_cblk % a.cpg == 0 && C % force_cblk == 0 && force_cblk % 4 == 0) {
       cblk = force_cblk;
     } else {
-      while ((size_t)HW * cblk * 4 > (size_t)8 * slab_kb * 1024 && cblk % 2 == 0 && (cblk / 2) % a.cpg == 0 && (cblk / 2) % 8 == 0 &&
-             (!x2 || C1 % (cblk / 2) == 0))
-        cblk /= 2;
+      while ((size_t)HW * cblk * 4 > (size_t)4 * slab_kb * 1024 && cblk / 2 >= 16 && can_halve(cblk)) cblk /= 2;
+      while ((size_t)HW * cblk * 4 > (size_t)8 * slab_kb * 1024 && cblk / 2 >= 8 && can_halve(cblk)) cblk /= 2;
     }
     a.cblk = cblk;
     const int q = cblk / 4;
