@@ -457,25 +457,58 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
         recs, fu.TIMING = fu.TIMING, None
         by = {}
-        for name, nbytes, e0, e1 in recs:
+        for name, nbytes, e0, e1, _ in recs:
             d = by.setdefault(name, [0, 0.0, 0, 0.0, 0])
             ms = e0.elapsed_time(e1)
             d[0] += nbytes; d[1] += ms; d[2] += 1
             if nbytes >= 64 * 1024 * 1024:                      # the launches that are not latency-bound
                 d[3] += ms; d[4] += nbytes
         k5 = by.get("K5", [0, 1e-9, 0, 0.0, 0])
+
+        # The kernel's own duration: the SAME launches (same tensors, same order) replayed from one CUDA graph, as they run
+        # inside the timed steps -- an event pair around an eager launch adds ~3 us to kernels that take 4-60 us.
+        def graph_ms(launches, reps=5):
+            if not launches:
+                return None
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for l in launches:
+                    l()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for l in launches:
+                    l()
+            g.replay()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1) / reps
+        k5_all = [r[4] for r in recs if r[0] == "K5"]
+        k5_big = [r[4] for r in recs if r[0] == "K5" and r[1] >= 64 * 1024 * 1024]
+        ms_all, ms_big = graph_ms(k5_all), graph_ms(k5_big)
+        ach = k5[0] / (ms_all * 1e-3) / 1e9 if ms_all else 0.0
         roofline_glue = {"kernel": "groupnorm_nhwc_cluster_kernel (K5: fused GroupNorm + SiLU + adds, NHWC)", "bound": "hbm",
-                         "achieved": k5[0] / (k5[1] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": k5[0] / (k5[1] * 1e-3) / 1e9 / pk["hbm_gbs"],
+                         "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
                          "traffic": ncu_traffic("groupnorm_nhwc_cluster_kernel B=64 C=128 64x64"),
                          "traffic_note": "ncu DRAM bytes of ONE launch at the largest shape (algorithmic 268 435 456 B)",
                          "peak_source": pk["source"] + " (burst copy bandwidth)",
-                         "bytes_per_forward": k5[0], "ms_per_forward": k5[1], "launches_timed": k5[2],
-                         "achieved_large_launches": (k5[4] / (k5[3] * 1e-3) / 1e9) if k5[3] > 0 else None,
-                         "note": "all K5 launches of one eager forward, algorithmic bytes = read x once + write y "
-                                 "once; each launch carries ~3 us of event overhead; 'large' = launches moving >= 64 MiB",
+                         "bytes_per_forward": k5[0], "ms_per_forward": ms_all, "launches_timed": k5[2],
+                         "achieved_large_launches": (k5[4] / (ms_big * 1e-3) / 1e9) if ms_big else None,
+                         "eager_event_pairs": {"ms_per_forward": k5[1], "gbs": k5[0] / (k5[1] * 1e-3) / 1e9,
+                                               "gbs_large_launches": (k5[4] / (k5[3] * 1e-3) / 1e9) if k5[3] > 0 else None},
+                         "note": "all K5 launches of one forward (same tensors, same order) replayed from one CUDA graph, CUDA "
+                                 "events around 5 replays; algorithmic bytes = read x once + write y once; 'large' = the "
+                                 "launches moving >= 64 MiB; eager_event_pairs = the same launches timed one by one in an "
+                                 "eager forward (each pair adds ~3 us)",
                          "others": {k: {"launches": v[2], "ms_per_forward": v[1], "gbs": v[0] / (v[1] * 1e-3) / 1e9}
                                     for k, v in by.items() if k != "K5"}}
+        del recs, k5_all, k5_big
 
     # ---- end to end through the public API with host buffers
     ms_e2e, _ = timed(step_e2e)

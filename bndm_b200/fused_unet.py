@@ -32,7 +32,8 @@ from .unet import UNet2DModel, UNet2DOutput, timestep_embedding
 
 LAUNCHES = 0      # launches of libbndm_b200.so kernels issued from this module (host-side count)
 TIMING = None     # when a list: every K5 / K6 / K7 launch is bracketed by CUDA events on its stream and
-                  # (name, algorithmic bytes, start event, end event) is appended (bench.py's live roofline)
+                  # (name, algorithmic bytes, start event, end event, launch closure) is appended (bench.py's live
+                  # roofline replays the closures -- same tensors -- from one CUDA graph)
 
 
 def _timed_launch(name, nbytes, device, launch):
@@ -42,7 +43,7 @@ def _timed_launch(name, nbytes, device, launch):
     e0.record(torch.cuda.current_stream(device))
     rc = launch()
     e1.record(torch.cuda.current_stream(device))
-    TIMING.append((name, nbytes, e0, e1))
+    TIMING.append((name, nbytes, e0, e1, launch))
     return rc
 
 
