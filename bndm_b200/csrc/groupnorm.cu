@@ -244,8 +244,14 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 // the HBM reads of item i+1 overlap the writes of item i; without this all resident CTAs moved in
 // lock step (load, compute, store) and DRAM sat idle two thirds of the time (ncu: 33 %).
 // kCluster = false: P == 1 (small activations), launched without a cluster; block barriers only.
-template <bool kCluster>
+// kPiped (the cluster launches): the slab moves in four cp.async commit groups, see below; the small single-CTA launches
+// have one to four iterations per thread and keep one group (the extra waits and commits cost them 10-15 %).
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool kCluster, bool kPiped = kCluster>
 __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(GnArgs a, int P, int ppc, int n_items) {
+  constexpr int NG = kPiped ? 4 : 1;                // commit groups per slab
   extern __shared__ __align__(16) float4 tile[];   // [pixels of this CTA][q] channel quads
   __shared__ Moments s_part[kGnMaxThreads];
   __shared__ Moments s_grp[2][32];                  // this CTA's moments per group, double-buffered by item parity
@@ -278,14 +284,24 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
     step = (size_t)pstep * (srow >> 2);
   };
 
+  // A thread's slots (i = tid + k nt) are loaded, read and refilled by that thread alone, in k order, so the slab is
+  // pipelined in four commit groups: the moments of the first quarter start while the later quarters are still landing
+  // (one wait for the whole slab exposed the full HBM latency once per item: 12 % of the warp samples in ncu).
+  const int kq = ((n_quads + nt - 1) / nt + NG - 1) / NG > 0 ? ((n_quads + nt - 1) / nt + NG - 1) / NG : 1;      // iterations per group
+
   int item = cluster_id;
   if (item < n_items) {
     const float4 *src;
     size_t step;
     src_of(item, src, step);
-    for (int i = tid; i < n_quads; i += nt, src += step) cp_async16(&tile[i], src);
+    for (int k = 0, i = tid; k < NG * kq; ++k, i += nt, src += step) {
+      if (i < n_quads) cp_async16(&tile[i], src);
+      if ((k + 1) % kq == 0) asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  } else {
+#pragma unroll
+    for (int g4 = 0; g4 < NG; ++g4) asm volatile("cp.async.commit_group;" ::: "memory");
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
 
   for (int par = 0; item < n_items; item += n_clusters, par ^= 1) {
     const int b = item / n_cblk, c0 = (item - b * n_cblk) * a.cblk;
@@ -294,21 +310,28 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
     if (a.add_bc) add = __ldg(reinterpret_cast<const float4 *>(a.add_bc + (size_t)b * a.add_stride + c));
     const float4 w = __ldg(reinterpret_cast<const float4 *>(a.weight + c));
     const float4 bi = __ldg(reinterpret_cast<const float4 *>(a.bias + c));
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-
     // ---- moments of this CTA's slab (s = x + add is written back so the second pass reads s) -----
+    // (no block barrier: every slot is touched by one thread only; s_grp / s_mean are ordered by the barriers below)
     float shift = 0.f, sum = 0.f, sq = 0.f, cnt = 0.f;
+    cp_async_wait<NG - 1>();
     if (tid < n_quads) shift = tile[tid].x + add.x;
+#pragma unroll
+    for (int g4 = 0; g4 < NG; ++g4) {
+      if (g4 == 1) cp_async_wait<2>();
+      if (g4 == 2) cp_async_wait<1>();
+      if (g4 == 3) cp_async_wait<0>();
 #pragma unroll 4
-    for (int i = tid; i < n_quads; i += nt) {
-      float4 s = tile[i];
-      s.x += add.x; s.y += add.y; s.z += add.z; s.w += add.w;
-      if (a.add_bc) tile[i] = s;
-      const float d0 = s.x - shift, d1 = s.y - shift, d2 = s.z - shift, d3 = s.w - shift;
-      sum += (d0 + d1) + (d2 + d3);
-      sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-      cnt += 4.f;
+      for (int k = 0; k < kq; ++k) {
+        const int i = tid + (g4 * kq + k) * nt;
+        if (i >= n_quads) break;
+        float4 s = tile[i];
+        s.x += add.x; s.y += add.y; s.z += add.z; s.w += add.w;
+        if (a.add_bc) tile[i] = s;
+        const float d0 = s.x - shift, d1 = s.y - shift, d2 = s.z - shift, d3 = s.w - shift;
+        sum += (d0 + d1) + (d2 + d3);
+        sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+        cnt += 4.f;
+      }
     }
     Moments m;
     m.n = cnt;
@@ -349,22 +372,28 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
     const float4 *nsrc = nullptr;
     size_t nstep = 0;
     if (next < n_items) src_of(next, nsrc, nstep);
+#pragma unroll
+    for (int g4 = 0; g4 < NG; ++g4) {
 #pragma unroll 4
-    for (int i = tid; i < n_quads; i += nt, y4 += ystep) {
-      const float4 s = tile[i];
-      if (nsrc) {
-        cp_async16(&tile[i], nsrc);
-        nsrc += nstep;
+      for (int k = 0; k < kq; ++k) {
+        const int i = tid + (g4 * kq + k) * nt;
+        if (i >= n_quads) break;
+        const float4 s = tile[i];
+        if (nsrc) {
+          cp_async16(&tile[i], nsrc);
+          nsrc += nstep;
+        }
+        float4 o;
+        o.x = fmaf(s.x, sc.x, sh.x);
+        o.y = fmaf(s.y, sc.y, sh.y);
+        o.z = fmaf(s.z, sc.z, sh.z);
+        o.w = fmaf(s.w, sc.w, sh.w);
+        if (a.silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+        *y4 = o;
+        y4 += ystep;
       }
-      float4 o;
-      o.x = fmaf(s.x, sc.x, sh.x);
-      o.y = fmaf(s.y, sc.y, sh.y);
-      o.z = fmaf(s.z, sc.z, sh.z);
-      o.w = fmaf(s.w, sc.w, sh.w);
-      if (a.silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
-      *y4 = o;
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    asm volatile("cp.async.commit_group;" ::: "memory");
   }
   if (kCluster) cluster.sync();                     // nobody leaves while a peer may still read its moments
 }
