@@ -820,6 +820,22 @@ int bndm_groupnorm_nhwc_f32(const float *x, const float *x2, int C1, const float
   return BNDM_OK;
 }
 
+int bndm_linear_tc_f32(const float *a, const float *w, const float *bias, float *out, int M, int N, int K, void *stream) {
+  if (!a || !w || !out || M < 1 || N < 1 || K < 1) { set_error("linear_tc: bad argument"); return BNDM_ERR_ARG; }
+  if (K % 32 != 0 || N % 4 != 0) {
+    set_error("linear_tc: K must be a multiple of 32 and N of 4 (M=%d N=%d K=%d)", M, N, K);
+    return BNDM_ERR_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(out)) % 16 != 0) {
+    set_error("linear_tc: pointers must be 16-byte aligned");
+    return BNDM_ERR_ARG;
+  }
+  cudaError_t e = launch_linear_tc(a, w, bias, out, M, N, K, (cudaStream_t)stream);
+  if (e == cudaErrorNotSupported) { set_error("linear_tc: unsupported shape M=%d N=%d K=%d", M, N, K); return BNDM_ERR_UNSUPPORTED; }
+  CK(e);
+  return BNDM_OK;
+}
+
 int bndm_snapshot_uint8_hwc(const float *x, uint8_t *out, int N, int C, int H, int W, const int *final_flags, int final_all,
                             void *stream) {
   if (!x || !out || N < 1 || C < 1 || H < 1 || W < 1) { set_error("snapshot_uint8: bad argument"); return BNDM_ERR_ARG; }

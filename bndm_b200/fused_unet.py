@@ -131,6 +131,32 @@ def attention_small(qkv, C, head_dim=8):
     return out
 
 
+def linear_tc(x, w, bias=None):
+    """F.linear(x, w, bias) for CUDA fp32 tensors on the tensor cores with fp32-grade results (K9, 3xTF32)."""
+    K = x.shape[-1]
+    a = x.reshape(-1, K)
+    if not a.is_contiguous():
+        a = a.contiguous()
+    if not w.is_contiguous():
+        w = w.contiguous()
+    M, N = a.shape[0], w.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _timed_launch("K9", 4 * (a.numel() + w.numel() + out.numel()), x.device, lambda: _lib.load().bndm_linear_tc_f32(
+            _lib.ptr(a), _lib.ptr(w), _lib.ptr(bias), _lib.ptr(out), M, N, K, _lib.current_stream(x.device)))
+    _lib.check(rc, "bndm_linear_tc_f32")
+    global LAUNCHES
+    LAUNCHES += 1
+    return out.reshape(*x.shape[:-1], N)
+
+
+def _use_linear_tc(x, w):
+    """K9 where it pays (>= 256 rows) and where the convolutions around it run in TF32 anyway (the reference's
+    configuration); with TF32 switched off the linears stay torch's fp32 GEMMs so the isolation tests compare like with like."""
+    return (x.is_cuda and x.dtype == torch.float32 and torch.backends.cudnn.allow_tf32 and x.numel() // x.shape[-1] >= 256
+            and x.shape[-1] % 32 == 0 and w.shape[0] % 4 == 0)
+
+
 class FusedUNet2D(torch.nn.Module):
     def __init__(self, model: UNet2DModel):
         super().__init__()
@@ -224,7 +250,7 @@ class FusedUNet2D(torch.nn.Module):
         y = groupnorm_silu_nhwc(x, att.group_norm, silu=False)
         h = y.permute(0, 2, 3, 1).reshape(B, H * W, C)
         wqkv, bqkv = self._qkv[id(att)]
-        qkv = F.linear(h, wqkv, bqkv)                                       # (B, HW, 3C)
+        qkv = linear_tc(h, wqkv, bqkv) if _use_linear_tc(h, wqkv) else F.linear(h, wqkv, bqkv)      # (B, HW, 3C)
         if C // att.heads == 8 and H * W <= 64:
             o = attention_small(qkv, C)                                     # K7
         else:
@@ -233,7 +259,8 @@ class FusedUNet2D(torch.nn.Module):
             def split(t):
                 return t.reshape(B, H * W, att.heads, C // att.heads).transpose(1, 2)
             o = F.scaled_dot_product_attention(split(q), split(k), split(v)).transpose(1, 2).reshape(B, H * W, C)
-        o = F.linear(o, att.to_out[0].weight, None)
+        wo = att.to_out[0].weight
+        o = linear_tc(o, wo) if _use_linear_tc(o, wo) else F.linear(o, wo, None)
         o = o.reshape(B, H, W, C).permute(0, 3, 1, 2)                      # channels-last view
         return add_bias_residual_nhwc(x, o, att.to_out[0].bias)
 

@@ -223,6 +223,13 @@ int bndm_upsample2x_nhwc_f32(const float *x, float *y, int B, int H, int W, int 
  * out dev [B][T][C].  head_dim must be 8, T <= 64.  Replaces F.scaled_dot_product_attention there. */
 int bndm_attention_small_f32(const float *qkv, float *out, int B, int T, int C, int head_dim, void *stream);
 
+/* K9 -- the fp32 linears of the UNet's attention blocks (diffusers Attention to_q/to_k/to_v/to_out; torch.nn.Linear
+ * semantics, which the reference runs as fp32 SIMT GEMMs: torch.backends.cuda.matmul.allow_tf32 is False) as a 3xTF32
+ * tcgen05 GEMM with fp32-grade results:   out[m][n] = sum_k a[m][k] * w[n][k] (+ bias[n]).
+ * a dev [M][K], w dev [N][K] (the Linear's weight), bias dev [N] or NULL, out dev [M][N]; K % 32 == 0, N % 4 == 0,
+ * a / w / out 16-byte aligned.                                                                                      */
+int bndm_linear_tc_f32(const float *a, const float *w, const float *bias, float *out, int M, int N, int K, void *stream);
+
 /* K6 -- out = ((a [+ a2]) [+ bias_a[c]]) + (b + bias_b[c]) on NHWC fp32 activations (n elements, C
  * channels innermost; a2 and bias_a may be NULL): the biases of conv_shortcut / conv2 (or an attention block's
  * to_out) and the residual add in one pass, same association as PyTorch's conv-bias then add.

@@ -66,6 +66,8 @@ def _pair(which):
     torch.manual_seed(0)
     if which == "cat_res64":
         model, x = get_model(3, 6, 64).to(DEV).eval(), torch.randn(4, 3, 64, 64, device=DEV)
+    elif which == "cat_res64_b16":         # 16 x 16 tokens = 256 rows: the attention linears take K9 (3xTF32 tcgen05)
+        model, x = get_model(3, 6, 64).to(DEV).eval(), torch.randn(16, 3, 64, 64, device=DEV)
     elif which == "cat_res128":
         model, x = get_model(3, 6, 128).to(DEV).eval(), torch.randn(2, 3, 128, 128, device=DEV)
     else:
@@ -87,7 +89,7 @@ def test_fused_unet_equals_stock_without_tf32(which, no_tf32):
     assert err <= 1e-5 * scale, (err, scale)
 
 
-@pytest.mark.parametrize("which", ["cat_res64", "latent512"])
+@pytest.mark.parametrize("which", ["cat_res64", "cat_res64_b16", "latent512"])
 def test_fused_unet_vs_stock_with_tf32(which):
     """torch's default (TF32 convolutions allowed, as the reference runs): the two evaluations use different cuDNN TF32
     kernels (NHWC vs NCHW), each within TF32's 2^-11 operand rounding of the fp32 result."""

@@ -230,6 +230,39 @@ def test_groupnorm_two_sources_equals_cat(B, C1, C2, H):
     assert torch.equal(got, want)
 
 
+# ---- K9: the attention blocks' fp32 linears as a 3xTF32 tcgen05 GEMM (csrc/linear_tc.cu) ----
+@pytest.mark.parametrize("M,N,K", [(1024, 1536, 512), (1024, 512, 512), (256, 1536, 512), (300, 516, 96), (128, 128, 32), (4096, 768, 256)])
+@pytest.mark.parametrize("with_bias", [True, False])
+def test_linear_tc_is_fp32_grade(M, N, K, with_bias):
+    """out = a w^T (+ bias): the error against an fp64 product stays at the level of torch's fp32 GEMM (what the reference
+    runs) and orders of magnitude under a single TF32 pass."""
+    from bndm_b200.fused_unet import linear_tc
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device=DEV) * 1.3 + 0.2
+    w = torch.randn(N, K, device=DEV) / K ** 0.5
+    b = torch.randn(N, device=DEV) if with_bias else None
+    got = linear_tc(a, w, b)
+    want64 = torch.nn.functional.linear(a.double(), w.double(), None if b is None else b.double())
+    old = torch.backends.cuda.matmul.allow_tf32
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ref32 = torch.nn.functional.linear(a, w, b)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        tf32 = torch.nn.functional.linear(a, w, b)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    scale = want64.abs().max().item()
+    err = (got.double() - want64).abs().max().item()
+    err32 = (ref32.double() - want64).abs().max().item()
+    err_tf32 = (tf32.double() - want64).abs().max().item()
+    assert err <= max(4.0 * err32, 2e-6 * scale), (err, err32, err_tf32, scale)
+    assert err * 20 < err_tf32 or err_tf32 < 1e-5 * scale, (err, err_tf32)
+    assert torch.equal(linear_tc(a, w, b), got)
+    # 3-D input (batch, tokens, features), as the attention block passes it
+    if M % 16 == 0:
+        assert torch.equal(linear_tc(a.view(M // 16, 16, K), w, b).reshape(M, N), got)
+
+
 def test_add_bias_residual_nhwc_is_bit_exact():
     from bndm_b200.fused_unet import add_bias_residual_nhwc
     a = torch.randn(3, 128, 16, 16, device=DEV).contiguous(memory_format=torch.channels_last)
