@@ -408,6 +408,83 @@ __global__ void __launch_bounds__(kGnMaxThreads) groupnorm_nhwc_cluster_kernel(G
   if (kCluster) cluster.sync();                     // nobody leaves while a peer may still read its moments
 }
 
+// ---- warp variant (the 2x2 / 4x4 / 8x8 levels) ------------------------------------------------
+// At the UNet's low resolutions a work item (sample, 32-channel block) is 0.5-8 KiB: staging it in shared memory and
+// meeting at block barriers costs more than moving it (4-10 us per launch for 2-17 MB).  Here ONE WARP owns an item in
+// registers: every lane loads its <= KMAX channel quads with independent 16-byte loads, the moments are merged by
+// shuffles only (lanes that share a quad, then the quads of a group; lower lane = left operand: fixed order), and the
+// lanes normalise and store what they hold.  No shared memory, no barrier, all items of a launch in flight at once.
+template <int KMAX>
+__global__ void __launch_bounds__(256) groupnorm_nhwc_warp_kernel(GnArgs a, int n_items) {
+  const int lane = threadIdx.x & 31;
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= n_items) return;
+  const int n_cblk = a.C >> 5;
+  const int b = item / n_cblk, c0 = (item - b * n_cblk) << 5;
+  const int cq = lane & 7, prow = lane >> 3;      // 8 quads per pixel, 4 pixels per pass
+  const int c = c0 + cq * 4;
+  const bool second = a.x2 != nullptr && c >= a.C1;
+  const int srow = second ? a.C - a.C1 : a.C1;
+  const float *sbase = second ? a.x2 + (c - a.C1) : a.x + c;
+  const float4 *src = reinterpret_cast<const float4 *>(sbase + ((size_t)b * a.HW + prow) * srow);
+  const size_t sstep = (size_t)srow;             // float4 units between passes: 4 pixels x srow floats / 4
+  float4 v[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (prow + 4 * k < a.HW) v[k] = __ldg(src + (size_t)k * sstep);
+  float4 add = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.add_bc) add = __ldg(reinterpret_cast<const float4 *>(a.add_bc + (size_t)b * a.add_stride + c));
+  const float4 w = __ldg(reinterpret_cast<const float4 *>(a.weight + c));
+  const float4 bi = __ldg(reinterpret_cast<const float4 *>(a.bias + c));
+
+  float shift = 0.f, sum = 0.f, sq = 0.f, cnt = 0.f;
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (prow + 4 * k < a.HW) {
+      v[k].x += add.x; v[k].y += add.y; v[k].z += add.z; v[k].w += add.w;
+      if (k == 0) shift = v[0].x;
+      const float d0 = v[k].x - shift, d1 = v[k].y - shift, d2 = v[k].z - shift, d3 = v[k].w - shift;
+      sum += (d0 + d1) + (d2 + d3);
+      sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+      cnt += 4.f;
+    }
+  Moments m;
+  m.n = cnt;
+  m.mean = cnt > 0.f ? shift + sum / cnt : 0.f;
+  m.m2 = cnt > 0.f ? fmaxf(sq - sum * sum / cnt, 0.f) : 0.f;
+  const int qpg = a.cpg >> 2;                    // quads per group: 1, 2, 4 or 8
+  // lanes that share a quad (xor 8, 16), then the quads of a group (xor 1 .. qpg / 2)
+  for (int off = 8; off < 32; off <<= 1) {
+    Moments o;
+    o.n = __shfl_xor_sync(0xffffffffu, m.n, off);
+    o.mean = __shfl_xor_sync(0xffffffffu, m.mean, off);
+    o.m2 = __shfl_xor_sync(0xffffffffu, m.m2, off);
+    m = (lane & off) ? merge(o, m) : merge(m, o);
+  }
+  for (int off = 1; off < qpg; off <<= 1) {
+    Moments o;
+    o.n = __shfl_xor_sync(0xffffffffu, m.n, off);
+    o.mean = __shfl_xor_sync(0xffffffffu, m.mean, off);
+    o.m2 = __shfl_xor_sync(0xffffffffu, m.m2, off);
+    m = (lane & off) ? merge(o, m) : merge(m, o);
+  }
+  const float rstd = rsqrtf(m.m2 / m.n + a.eps);
+  const float4 sc = make_float4(rstd * w.x, rstd * w.y, rstd * w.z, rstd * w.w);
+  const float4 sh = make_float4(bi.x - m.mean * sc.x, bi.y - m.mean * sc.y, bi.z - m.mean * sc.z, bi.w - m.mean * sc.w);
+  float4 *y4 = reinterpret_cast<float4 *>(a.y + ((size_t)b * a.HW + prow) * a.C + c);
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    if (prow + 4 * k < a.HW) {
+      float4 o;
+      o.x = fmaf(v[k].x, sc.x, sh.x);
+      o.y = fmaf(v[k].y, sc.y, sh.y);
+      o.z = fmaf(v[k].z, sc.z, sh.z);
+      o.w = fmaf(v[k].w, sc.w, sh.w);
+      if (a.silu) { o.x = silu_f(o.x); o.y = silu_f(o.y); o.z = silu_f(o.z); o.w = silu_f(o.w); }
+      y4[(size_t)k * a.C] = o;                    // 4 pixels further: 4 x C floats = C float4
+    }
+}
+
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
 // K6: out = (a [+ bias_a[c]]) + (b + bias_b[c]) on NHWC activations: the biases of conv_shortcut /
@@ -468,6 +545,20 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
   const int threads = kGnMaxThreads / q * q;
   const int cblk0 = cblk;                          // the register kernel below keeps whole 128-byte lines
 
+  if (!res && !sum_out && cblk == 32 && HW <= 64) {
+    // warp path: the 2x2 / 4x4 / 8x8 levels, one warp per (sample, 32-channel block)
+    static thread_local int warp_path = -1;    // BNDM_GN_WARP=0 switches it off (A/B measurements)
+    if (warp_path < 0) { const char *e = getenv("BNDM_GN_WARP"); warp_path = e ? atoi(e) : 1; }
+    const int qpg = a.cpg >> 2;
+    if (warp_path && (qpg == 1 || qpg == 2 || qpg == 4 || qpg == 8)) {
+      const int n_items = B * (C / 32);
+      const int blocks = (n_items + 7) / 8;
+      if (HW <= 4) groupnorm_nhwc_warp_kernel<1><<<blocks, 256, 0, s>>>(a, n_items);
+      else if (HW <= 16) groupnorm_nhwc_warp_kernel<4><<<blocks, 256, 0, s>>>(a, n_items);
+      else groupnorm_nhwc_warp_kernel<16><<<blocks, 256, 0, s>>>(a, n_items);
+      return cudaGetLastError();
+    }
+  }
   if (!res && !sum_out) {
     // cluster path: P CTAs per (sample, channel block), slab of HW / P pixels in shared memory
     static thread_local int slab_kb = 0;      // BNDM_GN_SLAB_KB: target slab size per CTA (experiments); default 64
