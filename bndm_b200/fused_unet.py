@@ -265,6 +265,8 @@ class FusedUNet2D(torch.nn.Module):
         return add_bias_residual_nhwc(x, o, att.to_out[0].bias)
 
     def _down(self, block, h, temb_act, h_bias=None):
+        """Returns (h, skips, bias still owed to h): the downsampler's convolution runs without its bias; the next block's
+        first resnet and the skip's consumer absorb it (like conv_in's)."""
         skips = []
         for i, resnet in enumerate(block.resnets):
             h = self._resnet(resnet, h, temb_act, x_bias=h_bias if i == 0 else None)
@@ -272,9 +274,11 @@ class FusedUNet2D(torch.nn.Module):
                 h = self._attention(block.attentions[i], h)
             skips.append((h, None))
         if block.downsamplers is not None:
-            h = block.downsamplers[0](h)
-            skips.append((h, None))
-        return h, skips
+            conv = block.downsamplers[0].conv
+            h = F.conv2d(h, conv.weight, None, stride=2, padding=1)
+            skips.append((h, conv.bias))
+            return h, skips, conv.bias
+        return h, skips, None
 
     def _up(self, block, h, skips, temb_act, h_bias=None):
         """Returns (h, bias still owed to h): the upsampler's convolution runs without its bias, the next
@@ -319,8 +323,9 @@ class FusedUNet2D(torch.nn.Module):
         # conv_in's bias is owed to h: the first resnet and the last skip consumer absorb it
         h = F.conv2d(sample.float().contiguous(memory_format=torch.channels_last), m.conv_in.weight, None, padding=1)
         skips = [(h, m.conv_in.bias)]
-        for i, block in enumerate(m.down_blocks):
-            h, s = self._down(block, h, temb_act, h_bias=m.conv_in.bias if i == 0 else None)
+        owed = m.conv_in.bias
+        for block in m.down_blocks:
+            h, s, owed = self._down(block, h, temb_act, h_bias=owed)
             skips.extend(s)
         h = self._resnet(m.mid_block.resnets[0], h, temb_act)
         h = self._attention(m.mid_block.attentions[0], h)
