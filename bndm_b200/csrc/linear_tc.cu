@@ -15,9 +15,11 @@
 // warps write the lo tiles next to them in shared memory (the kernel is bound by the bytes TMA delivers to an SM, so the lo
 // parts are never read from memory), the large main sums and the small corrections accumulate in separate TMEM columns and
 // meet in fp32 registers in the epilogue.  Measured (tools/linear_probe.py, B200): 17.5 us for every shape of the UNet
-// (M = 256..1024, N = 512..1536, K = 512: 44.7 / 19.8 / 19.0 us in torch) -- a CTA's 16 stages are a latency chain (TMA from
-// L2 -> converter -> 12 MMAs -> stage free, ~3 us over a 3-deep ring of 64 KiB stages), not a bandwidth or tensor limit; a per-CTA
-// k offset against L2 hot-spotting changed nothing.  max|err| against fp64 ~2x torch's fp32 GEMM (64 k-steps accumulate in TMEM).
+// (M = 256..1024, N = 512..1536, K = 512: 44.7 / 19.8 / 19.0 us in torch).  The bound is SHARED-MEMORY BANDWIDTH, as for K1b:
+// per 32-k stage the three MMAs of each of the 4 k-steps read 8 KiB of operands each (96 KiB), the converter reads and
+// writes 64 KiB, TMA writes 32 KiB -- 192 KiB at 128 B/clk = 1536 cycles against 768 cycles of tensor work; a 4-deep raw ring
+// with a separate lo ring (more loads in flight) and a per-CTA k offset (L2 hot-spotting) changed nothing, which is what
+// a shared-memory bound predicts.  max|err| against fp64 ~2x torch's fp32 GEMM (64 k-steps accumulate in TMEM).
 // CTA: warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2..5 = epilogue (one TMEM lane quarter each),
 // warps 6..9 = converter.
 #include <cuda.h>
