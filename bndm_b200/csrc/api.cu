@@ -836,6 +836,24 @@ int bndm_linear_tc_f32(const float *a, const float *w, const float *bias, float 
   return BNDM_OK;
 }
 
+int bndm_shortcut_residual_tf32(const float *x, const float *x2, int C1, int C2, const float *w, const float *h2, const float *bias,
+                                float *out, int64_t M, int N, void *stream) {
+  if (!x || !w || !h2 || !out || M < 1 || N < 1 || C1 < 1 || C2 < 0 || (C2 > 0 && !x2)) { set_error("shortcut_residual: bad argument"); return BNDM_ERR_ARG; }
+  if (C1 % 32 != 0 || C2 % 32 != 0 || N % 4 != 0) {
+    set_error("shortcut_residual: C1 and C2 must be multiples of 32 and N of 4 (C1=%d C2=%d N=%d)", C1, C2, N);
+    return BNDM_ERR_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(h2) |
+       reinterpret_cast<uintptr_t>(out)) % 16 != 0) {
+    set_error("shortcut_residual: pointers must be 16-byte aligned");
+    return BNDM_ERR_ARG;
+  }
+  cudaError_t e = launch_shortcut_tc(x, x2, C1, C2, w, h2, bias, out, (long long)M, N, (cudaStream_t)stream);
+  if (e == cudaErrorNotSupported) { set_error("shortcut_residual: unsupported shape M=%lld N=%d", (long long)M, N); return BNDM_ERR_UNSUPPORTED; }
+  CK(e);
+  return BNDM_OK;
+}
+
 int bndm_snapshot_uint8_hwc(const float *x, uint8_t *out, int N, int C, int H, int W, const int *final_flags, int final_all,
                             void *stream) {
   if (!x || !out || N < 1 || C < 1 || H < 1 || W < 1) { set_error("snapshot_uint8: bad argument"); return BNDM_ERR_ARG; }

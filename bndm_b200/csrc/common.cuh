@@ -282,6 +282,9 @@ cudaError_t launch_groupnorm_nhwc(const float *x, const float *x2, int C1, const
                                   int silu, cudaStream_t s);
 // K9 (linear_tc.cu): out[m][n] = sum_k a[m][k] w[n][k] (+ bias[n]) as a 3xTF32 tcgen05 GEMM
 cudaError_t launch_linear_tc(const float *a, const float *w, const float *bias, float *out, int M, int N, int K, cudaStream_t s);
+// K10 (shortcut_tc.cu): out[m][n] = sum_k w[n][k] cat(x, x2)[m][k] + h2[m][n] + bias[n] (1x1 convolution in TF32 + residual + biases)
+cudaError_t launch_shortcut_tc(const float *x, const float *x2, int C1, int C2, const float *w, const float *h2, const float *bias,
+                               float *out, long long M, int N, cudaStream_t s);
 cudaError_t launch_to_u8(const float *x, uint8_t *out, int B, int C, int HW, cudaStream_t s);
 cudaError_t launch_snapshot_u8(const float *x, uint8_t *out, int N, int C, int HW, const int *final_flags, int final_all,
                                cudaStream_t s);

@@ -150,6 +150,39 @@ def linear_tc(x, w, bias=None):
     return out.reshape(*x.shape[:-1], N)
 
 
+def shortcut_residual_nhwc(x, x2, w, h2, bias):
+    """conv1x1(cat(x, x2), w) + h2 + bias on channels-last (B,C,H,W) tensors in one kernel (K10): the shortcut convolution
+    of a ResnetBlock2D in TF32 on the tensor cores with the residual and both biases added in its epilogue."""
+    B, C1, H, W = x.shape
+    C2 = x2.shape[1] if x2 is not None else 0
+    N = w.shape[0]
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    if x2 is not None and not x2.is_contiguous(memory_format=torch.channels_last):
+        x2 = x2.contiguous(memory_format=torch.channels_last)
+    if not h2.is_contiguous(memory_format=torch.channels_last):
+        h2 = h2.contiguous(memory_format=torch.channels_last)
+    w2 = w.reshape(N, C1 + C2)
+    if not w2.is_contiguous():
+        w2 = w2.contiguous()
+    out = torch.empty_like(h2, memory_format=torch.channels_last)
+    M = B * H * W
+    with torch.cuda.device(x.device):
+        rc = _timed_launch("K10", 4 * (M * (C1 + C2) + 2 * M * N), x.device, lambda: _lib.load().bndm_shortcut_residual_tf32(
+            _lib.ptr(x), _lib.ptr(x2), C1, C2, _lib.ptr(w2), _lib.ptr(h2), _lib.ptr(bias), _lib.ptr(out), M, N,
+            _lib.current_stream(x.device)))
+    _lib.check(rc, "bndm_shortcut_residual_tf32")
+    global LAUNCHES
+    LAUNCHES += 1
+    return out
+
+
+def _use_shortcut_tc(x, x2, w):
+    """K10 replaces cuDNN's TF32 1x1 convolution, so only while TF32 convolutions are allowed (the reference's configuration)."""
+    return (x.is_cuda and x.dtype == torch.float32 and torch.backends.cudnn.allow_tf32 and x.shape[1] % 32 == 0
+            and (x2 is None or x2.shape[1] % 32 == 0) and w.shape[0] % 4 == 0 and x.shape[0] * x.shape[2] * x.shape[3] >= 256)
+
+
 def _use_linear_tc(x, w):
     """K9 where it pays (>= 256 rows) and where the convolutions around it run in TF32 anyway (the reference's
     configuration); with TF32 switched off the linears stay torch's fp32 GEMMs so the isolation tests compare like with like."""
@@ -210,6 +243,11 @@ class FusedUNet2D(torch.nn.Module):
         h = F.conv2d(y, blk.conv1.weight, None, padding=1)                 # bias folded into tb_all
         y2 = groupnorm_silu_nhwc(h, blk.norm2, add_bc=tb_all[0, lo:hi] if tb_all.shape[0] == 1 else tb_all[:, lo:hi])
         h2 = F.conv2d(y2, blk.conv2.weight, None, padding=1)               # bias added with the residual (K6)
+        if blk.conv_shortcut is not None and _use_shortcut_tc(x, x2, blk.conv_shortcut.weight):
+            # K10: the 1x1 shortcut convolution of [x | x2], the residual add and both biases in one kernel
+            if "tail_bias" not in pend:
+                pend["tail_bias"] = (pend["sc_bias"] + blk.conv2.bias).contiguous()
+            return shortcut_residual_nhwc(x, x2, blk.conv_shortcut.weight, h2, pend["tail_bias"])
         if x2 is not None:
             w1, w2 = self._sc_split(blk, x.shape[1])
             sc, sc2 = F.conv2d(x, w1, None), F.conv2d(x2, w2, None)

@@ -230,6 +230,16 @@ int bndm_attention_small_f32(const float *qkv, float *out, int B, int T, int C, 
  * a / w / out 16-byte aligned.                                                                                      */
 int bndm_linear_tc_f32(const float *a, const float *w, const float *bias, float *out, int M, int N, int K, void *stream);
 
+/* K10 -- the tail of a ResnetBlock2D with a 1x1 conv_shortcut (diffusers; every resnet of the up blocks, whose input is
+ * cat(h, skip)):   out[m][n] = sum_k w[n][k] * cat(x, x2)[m][k]  +  h2[m][n]  +  bias[n]
+ * i.e. the shortcut convolution (TF32 inputs, fp32 accumulation, as cuDNN runs it when torch.backends.cudnn.allow_tf32 is
+ * set -- the reference's configuration), the residual add and both biases in one tcgen05 kernel.
+ * x dev [M][C1], x2 dev [M][C2] or NULL with C2 = 0 (channels-last activations, M = B*H*W rows), w dev [N][C1 + C2] (the
+ * convolution's weight), h2 dev [M][N] (conv2's output without its bias), bias dev [N] or NULL (conv_shortcut.bias +
+ * conv2.bias), out dev [M][N] (may be h2).  C1 % 32 == 0, C2 % 32 == 0, N % 4 == 0.                                      */
+int bndm_shortcut_residual_tf32(const float *x, const float *x2, int C1, int C2, const float *w, const float *h2,
+                                const float *bias, float *out, int64_t M, int N, void *stream);
+
 /* K6 -- out = ((a [+ a2]) [+ bias_a[c]]) + (b + bias_b[c]) on NHWC fp32 activations (n elements, C
  * channels innermost; a2 and bias_a may be NULL): the biases of conv_shortcut / conv2 (or an attention block's
  * to_out) and the residual add in one pass, same association as PyTorch's conv-bias then add.

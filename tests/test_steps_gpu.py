@@ -263,6 +263,44 @@ def test_linear_tc_is_fp32_grade(M, N, K, with_bias):
         assert torch.equal(linear_tc(a.view(M // 16, 16, K), w, b).reshape(M, N), got)
 
 
+# ---- K10: 1x1 shortcut convolution of [x | x2] + residual + biases in one tcgen05 kernel (csrc/shortcut_tc.cu) ----
+@pytest.mark.parametrize("B,C1,C2,N,H", [(2, 128, 128, 128, 64), (2, 256, 128, 128, 32), (3, 512, 512, 512, 4), (2, 512, 256, 256, 8),
+                                         (2, 128, 0, 256, 16), (1, 128, 128, 128, 5), (5, 256, 256, 256, 16), (1, 96, 32, 132, 7)])
+def test_shortcut_residual_matches_the_tf32_convolution(B, C1, C2, N, H):
+    from bndm_b200.fused_unet import shortcut_residual_nhwc
+    torch.manual_seed(B + C1 + C2 + N + H)
+    cl = torch.channels_last
+    x = torch.randn(B, C1, H, H, device=DEV).contiguous(memory_format=cl)
+    x2 = torch.randn(B, C2, H, H, device=DEV).contiguous(memory_format=cl) if C2 else None
+    w = (torch.randn(N, C1 + C2, 1, 1, device=DEV) / (C1 + C2) ** 0.5).contiguous(memory_format=cl)
+    h2 = torch.randn(B, N, H, H, device=DEV).contiguous(memory_format=cl)
+    bias = torch.randn(N, device=DEV)
+    got = shortcut_residual_nhwc(x, x2, w, h2, bias)
+    assert got.shape == h2.shape and got.is_contiguous(memory_format=cl)
+    xc = x if x2 is None else torch.cat([x, x2], 1)
+    want64 = torch.nn.functional.conv2d(xc.double(), w.double()) + h2.double() + bias.double()[None, :, None, None]
+    old = torch.backends.cudnn.allow_tf32
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        lib = torch.nn.functional.conv2d(xc.contiguous(memory_format=cl), w) + h2 + bias[None, :, None, None]
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    err = (got.double() - want64).abs().max().item()
+    err_lib = (lib.double() - want64).abs().max().item()
+    # TF32 inputs, fp32 accumulation: the same class of error as the library's TF32 convolution (which may have picked an
+    # fp32 kernel for a small shape, hence the absolute floor at TF32's 2^-11 input rounding)
+    assert err <= max(3.0 * err_lib, 4e-3), (err, err_lib)
+    assert torch.equal(shortcut_residual_nhwc(x, x2, w, h2, bias), got)
+    # in place on the residual
+    h2c = h2.clone(memory_format=torch.preserve_format)
+    from bndm_b200 import _lib
+    M = B * H * H
+    rc = _lib.load().bndm_shortcut_residual_tf32(_lib.ptr(x), _lib.ptr(x2), C1, C2, _lib.ptr(w.reshape(N, C1 + C2).contiguous()), _lib.ptr(h2c),
+                                                 _lib.ptr(bias), _lib.ptr(h2c), M, N, _lib.current_stream(x.device))
+    _lib.check(rc, "bndm_shortcut_residual_tf32")
+    assert torch.equal(h2c, got)
+
+
 def test_add_bias_residual_nhwc_is_bit_exact():
     from bndm_b200.fused_unet import add_bias_residual_nhwc
     a = torch.randn(3, 128, 16, 16, device=DEV).contiguous(memory_format=torch.channels_last)
