@@ -178,9 +178,11 @@ def shortcut_residual_nhwc(x, x2, w, h2, bias):
 
 
 def _use_shortcut_tc(x, x2, w):
-    """K10 replaces cuDNN's TF32 1x1 convolution, so only while TF32 convolutions are allowed (the reference's configuration)."""
+    """K10 replaces cuDNN's TF32 1x1 convolution, so only while TF32 convolutions are allowed (the reference's configuration),
+    and where it is faster than the three kernels it replaces: from 8192 rows up (tools/shortcut_probe.py: 108.8 vs 171.7 us
+    at 64^2 x 128 channels and batch 64, 19.6 vs 27.3 us at 16^2; below, a CTA's K loop is a latency chain and cuDNN wins)."""
     return (x.is_cuda and x.dtype == torch.float32 and torch.backends.cudnn.allow_tf32 and x.shape[1] % 32 == 0
-            and (x2 is None or x2.shape[1] % 32 == 0) and w.shape[0] % 4 == 0 and x.shape[0] * x.shape[2] * x.shape[3] >= 256)
+            and (x2 is None or x2.shape[1] % 32 == 0) and w.shape[0] % 4 == 0 and x.shape[0] * x.shape[2] * x.shape[3] >= 8192)
 
 
 def _use_linear_tc(x, w):
