@@ -535,7 +535,7 @@ def run_ours(args):
             "gpu_launches": args.steps * (noise_calls * noise_launches + T * (1 + kpf)),
             "gpu_launches_note": f"per step: {noise_calls} x get_noise_v2 ({noise_launches} launches: "
                                  f"{'K1g' if n_cols <= 16 else 'K1a pack + K1b contraction + K1c combine'}) + {T} x (update kernel + "
-                                 f"{kpf} K5-K10 launches inside the UNet forward); cuDNN/cuBLAS/ATen kernels are not counted",
+                                 f"{kpf} K5-K11 launches inside the UNet forward); cuDNN/cuBLAS/ATen kernels are not counted",
             "clocks": clock_info,
             "checksum": checksum,
             # `roofline` = the kernel of libbndm_b200.so with the largest share of the step's device time: K5 when the

@@ -49,6 +49,7 @@ SIGNATURES = {
                                           C.c_float, C.c_int, _P]),
     "bndm_linear_tc_f32": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_shortcut_residual_tf32": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),
+    "bndm_conv_in3x3_nhwc_f32": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_upsample2x_nhwc_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_attention_small_f32": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "bndm_add_bias_nhwc_f32": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int, _P]),

@@ -854,6 +854,15 @@ int bndm_shortcut_residual_tf32(const float *x, const float *x2, int C1, int C2,
   return BNDM_OK;
 }
 
+int bndm_conv_in3x3_nhwc_f32(const float *x, const float *w, float *out, int B, int Cin, int H, int W, int Cout, void *stream) {
+  if (!x || !w || !out || B < 1 || Cin < 1 || H < 1 || W < 1 || Cout < 1) { set_error("conv_in3x3: bad argument"); return BNDM_ERR_ARG; }
+  if (reinterpret_cast<uintptr_t>(out) % 16 != 0) { set_error("conv_in3x3: out must be 16-byte aligned"); return BNDM_ERR_ARG; }
+  cudaError_t e = launch_conv_in3x3(x, w, out, B, Cin, H, W, Cout, (cudaStream_t)stream);
+  if (e == cudaErrorNotSupported) { set_error("conv_in3x3: unsupported shape Cin=%d Cout=%d", Cin, Cout); return BNDM_ERR_UNSUPPORTED; }
+  CK(e);
+  return BNDM_OK;
+}
+
 int bndm_snapshot_uint8_hwc(const float *x, uint8_t *out, int N, int C, int H, int W, const int *final_flags, int final_all,
                             void *stream) {
   if (!x || !out || N < 1 || C < 1 || H < 1 || W < 1) { set_error("snapshot_uint8: bad argument"); return BNDM_ERR_ARG; }

@@ -285,6 +285,8 @@ cudaError_t launch_linear_tc(const float *a, const float *w, const float *bias, 
 // K10 (shortcut_tc.cu): out[m][n] = sum_k w[n][k] cat(x, x2)[m][k] + h2[m][n] + bias[n] (1x1 convolution in TF32 + residual + biases)
 cudaError_t launch_shortcut_tc(const float *x, const float *x2, int C1, int C2, const float *w, const float *h2, const float *bias,
                                float *out, long long M, int N, cudaStream_t s);
+// K11 (conv_in.cu): 3x3 convolution of an NCHW input with <= 4 channels to an NHWC activation (no bias)
+cudaError_t launch_conv_in3x3(const float *x, const float *w, float *out, int B, int Cin, int H, int W, int Cout, cudaStream_t s);
 cudaError_t launch_to_u8(const float *x, uint8_t *out, int B, int C, int HW, cudaStream_t s);
 cudaError_t launch_snapshot_u8(const float *x, uint8_t *out, int N, int C, int HW, const int *final_flags, int final_all,
                                cudaStream_t s);

@@ -177,6 +177,24 @@ def shortcut_residual_nhwc(x, x2, w, h2, bias):
     return out
 
 
+def conv_in3x3_nhwc(x, w):
+    """conv2d(x, w, padding=1) for an NCHW fp32 input with <= 4 channels, written as a channels-last (B,Cout,H,W) tensor (K11);
+    ``w`` is the contiguous (Cout, Cin, 3, 3) weight.  None when the shape is not one the kernel takes."""
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    if Cin > 4 or Cout % 4 != 0 or 256 % (Cout // 4) != 0 or tuple(w.shape[1:]) != (Cin, 3, 3):
+        return None
+    x = x.contiguous()
+    out = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        rc = _timed_launch("K11", 4 * (x.numel() + out.numel()), x.device, lambda: _lib.load().bndm_conv_in3x3_nhwc_f32(
+            _lib.ptr(x), _lib.ptr(w), _lib.ptr(out), B, Cin, H, W, Cout, _lib.current_stream(x.device)))
+    _lib.check(rc, "bndm_conv_in3x3_nhwc_f32")
+    global LAUNCHES
+    LAUNCHES += 1
+    return out
+
+
 def _use_shortcut_tc(x, x2, w):
     """K10 replaces cuDNN's TF32 1x1 convolution, so only while TF32 convolutions are allowed (the reference's configuration),
     and where it is faster than the three kernels it replaces: from 8192 rows up (tools/shortcut_probe.py: 108.8 vs 171.7 us
@@ -215,6 +233,7 @@ class FusedUNet2D(torch.nn.Module):
             self._temb_slices[id(r)] = (off, off + n)
             off += n
 
+        self._conv_in_w = self.m.conv_in.weight.detach().contiguous().clone()      # (Cout, Cin, 3, 3) row-major for K11
         self._sc_w = {}
         self._pend = {}
         self._qkv = {}
@@ -361,7 +380,9 @@ class FusedUNet2D(torch.nn.Module):
         temb_act = torch.addmm(self.temb_b, temb_act, self.temb_w.t())      # (B or 1, sum of Cout): all projections
 
         # conv_in's bias is owed to h: the first resnet and the last skip consumer absorb it
-        h = F.conv2d(sample.float().contiguous(memory_format=torch.channels_last), m.conv_in.weight, None, padding=1)
+        h = conv_in3x3_nhwc(sample.float(), self._conv_in_w) if sample.is_cuda else None       # K11: NCHW state -> NHWC activation
+        if h is None:
+            h = F.conv2d(sample.float().contiguous(memory_format=torch.channels_last), m.conv_in.weight, None, padding=1)
         skips = [(h, m.conv_in.bias)]
         owed = m.conv_in.bias
         for block in m.down_blocks:

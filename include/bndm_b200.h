@@ -240,6 +240,12 @@ int bndm_linear_tc_f32(const float *a, const float *w, const float *bias, float 
 int bndm_shortcut_residual_tf32(const float *x, const float *x2, int C1, int C2, const float *w, const float *h2,
                                 const float *bias, float *out, int64_t M, int N, void *stream);
 
+/* K11 -- the UNet's first convolution (diffusers UNet2DModel.conv_in: 3x3, padding 1) from the sampler's NCHW state to the
+ * channels-last activation: out[b][h][w][co] = sum w[co][ci][r][s] * x[b][ci][h+r-1][w+s-1], fp32 FMA, no bias.
+ * x dev [B][Cin][H][W] (Cin <= 4), w dev [Cout][Cin][3][3] (contiguous), out dev [B][H][W][Cout]; Cout % 4 == 0 and
+ * 256 % (Cout / 4) == 0 (128 for every model of the reference), otherwise BNDM_ERR_UNSUPPORTED.                      */
+int bndm_conv_in3x3_nhwc_f32(const float *x, const float *w, float *out, int B, int Cin, int H, int W, int Cout, void *stream);
+
 /* K6 -- out = ((a [+ a2]) [+ bias_a[c]]) + (b + bias_b[c]) on NHWC fp32 activations (n elements, C
  * channels innermost; a2 and bias_a may be NULL): the biases of conv_shortcut / conv2 (or an attention block's
  * to_out) and the residual add in one pass, same association as PyTorch's conv-bias then add.

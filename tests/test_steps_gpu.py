@@ -301,6 +301,22 @@ def test_shortcut_residual_matches_the_tf32_convolution(B, C1, C2, N, H):
     assert torch.equal(h2c, got)
 
 
+# ---- K11: conv_in (3x3, <= 4 input channels) from the NCHW state to the channels-last activation (csrc/conv_in.cu) ----
+@pytest.mark.parametrize("B,Cin,H,W,Cout", [(2, 3, 64, 64, 128), (1, 4, 32, 32, 128), (3, 3, 5, 7, 128), (2, 3, 16, 50, 64), (1, 3, 128, 128, 128),
+                                            (2, 1, 9, 33, 32)])
+def test_conv_in3x3_matches_conv2d(B, Cin, H, W, Cout):
+    from bndm_b200.fused_unet import conv_in3x3_nhwc
+    torch.manual_seed(B + Cin + H + W + Cout)
+    x = torch.randn(B, Cin, H, W, device=DEV)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV) / (9 * Cin) ** 0.5
+    got = conv_in3x3_nhwc(x, w)
+    assert got is not None and got.shape == (B, Cout, H, W) and got.is_contiguous(memory_format=torch.channels_last)
+    want = torch.nn.functional.conv2d(x.double(), w.double(), padding=1)
+    assert (got.double() - want).abs().max().item() <= 1e-5
+    assert torch.equal(conv_in3x3_nhwc(x, w), got)
+    assert conv_in3x3_nhwc(torch.randn(1, 8, 4, 4, device=DEV), torch.randn(128, 8, 3, 3, device=DEV)) is None      # not a conv_in shape
+
+
 def test_add_bias_residual_nhwc_is_bit_exact():
     from bndm_b200.fused_unet import add_bias_residual_nhwc
     a = torch.randn(3, 128, 16, 16, device=DEV).contiguous(memory_format=torch.channels_last)

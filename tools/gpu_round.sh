@@ -6,7 +6,7 @@
 TAG=${1:-r02}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-KERNELS='gemv_kernel|gemm_tc_kernel|snapshot_u8|iadb_step_kernel|ddim_step_kernel|to_u8_kernel|pack_kernel|combine_kernel|groupnorm_nhwc|add_bias_nhwc|attention_small|upsample2x|linear_tc|shortcut_tc'
+KERNELS='gemv_kernel|gemm_tc_kernel|snapshot_u8|iadb_step_kernel|ddim_step_kernel|to_u8_kernel|pack_kernel|combine_kernel|groupnorm_nhwc|add_bias_nhwc|attention_small|upsample2x|linear_tc|shortcut_tc|conv_in3x3'
 keep_small() { if [ -f "$1" ] && [ $(stat -c %s "$1") -gt 20000000 ]; then rm -f "$1"; fi; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $OUT/gpu.txt 2>&1
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee $OUT/pytest_gpu.txt

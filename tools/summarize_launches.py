@@ -24,7 +24,7 @@ print(f"{len(rows)} launches, {total / 1e3:.3f} ms of device time (cold-cache, s
 print(f"{'kernel':92s} {'n':>6s} {'total_us':>12s} {'mean_us':>10s} {'share':>7s}")
 for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
     print(f"{k:92s} {n:6d} {us:12.1f} {us / n:10.2f} {100 * us / total:6.2f}%")
-ours = {k: v for k, v in agg.items() if any(s in k for s in ("gemv_kernel", "snapshot_u8", "gemm_tc", "gemm_simt", "iadb_step", "pack_kernel", "epilogue_kernel", "combine_kernel", "groupnorm_nhwc", "add_bias_nhwc", "attention_small", "linear_tc", "shortcut_tc", "upsample2x", "tile_L", "tri_check", "ddim_step", "to_u8", "white128"))}
+ours = {k: v for k, v in agg.items() if any(s in k for s in ("gemv_kernel", "snapshot_u8", "gemm_tc", "gemm_simt", "iadb_step", "pack_kernel", "epilogue_kernel", "combine_kernel", "groupnorm_nhwc", "add_bias_nhwc", "attention_small", "linear_tc", "shortcut_tc", "conv_in3x3", "upsample2x", "tile_L", "tri_check", "ddim_step", "to_u8", "white128"))}
 print("-- kernels of libbndm_b200.so")
 for k, (n, us) in sorted(ours.items(), key=lambda kv: -kv[1][1]):
     print(f"{k:92s} {n:6d} {us:12.1f} {us / n:10.2f} {100 * us / total:6.2f}%")
