@@ -14,7 +14,13 @@ weights into channels-last form) and evaluates the same network with
     of norm2 -- as ONE launch of ``bndm_groupnorm_nhwc_f32`` (csrc/groupnorm.cu),
   * conv1's bias folded into the per-sample time-embedding vector (a (B, C) add instead of a
     full activation pass), all 30 ``time_emb_proj`` linears evaluated as ONE GEMM per forward,
-  * conv2's bias and the residual add as one pass (``bndm_add_bias_nhwc_f32``).
+  * conv2's bias and the residual add as one pass (``bndm_add_bias_nhwc_f32``, K6) -- or, where the shortcut is a 1x1
+    convolution (every resnet of the up blocks), the shortcut GEMM of [h | skip], the residual add and both biases as ONE
+    TF32 tcgen05 kernel (``bndm_shortcut_residual_tf32``, K10),
+  * the attention blocks' fp32 q/k/v and output projections as a 3xTF32 tcgen05 GEMM (``bndm_linear_tc_f32``, K9),
+  * ``conv_in`` from the sampler's NCHW state straight to the channels-last activation (``bndm_conv_in3x3_nhwc_f32``, K11).
+K9 / K10 replace TF32-class library kernels and are used only while ``torch.backends.cudnn.allow_tf32`` is set (torch's
+default and the reference's configuration); with TF32 switched off every GEMM stays torch's.
 Same call conventions as the wrapped model (``model(x, t, return_dict=False)[0]`` /
 ``.sample``); inference only (no autograd through K5).  Results agree with the wrapped module
 to fp32 round-off of the normalisation (the convolutions are the same cuDNN TF32 kernels).
