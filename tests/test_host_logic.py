@@ -52,6 +52,17 @@ def test_product_refuses_cpu_tensors():
         bb.get_noise_v2(torch.device("cpu"), x, L, None, None, "nope")
 
 
+def test_fused_unet_gemm_paths_are_gated():
+    """K9 / K10 / K11 are CUDA-only fast paths: CPU tensors and unsupported shapes never reach the library."""
+    import torch
+    from bndm_b200 import fused_unet as fu
+    x = torch.randn(2, 128, 64, 64)
+    assert not fu._use_shortcut_tc(x, None, torch.randn(128, 128, 1, 1))
+    assert not fu._use_linear_tc(torch.randn(1024, 512), torch.randn(1536, 512))
+    assert fu.conv_in3x3_nhwc(torch.randn(1, 8, 4, 4), torch.randn(128, 8, 3, 3)) is None          # not a conv_in shape
+    assert fu.conv_in3x3_nhwc(torch.randn(1, 3, 4, 4), torch.randn(224, 3, 3, 3)) is None          # 256 % (224 / 4) != 0
+
+
 def test_product_does_not_import_oracle():
     src_dir = os.path.join(ROOT, "bndm_b200")
     for fn in os.listdir(src_dir):
@@ -337,6 +348,14 @@ def test_c_abi_rejects_bad_arguments_before_touching_the_device():
     assert lib.bndm_add_bias_nhwc_f32(fake, None, None, fake, fake, fake, 130, 128, None) == _lib.ERR_ARG   # n % C
     assert lib.bndm_upsample2x_nhwc_f32(fake, fake, 1, 4, 4, 6, None) == _lib.ERR_ARG                       # C % 4
     assert lib.bndm_attention_small_f32(None, fake, 1, 16, 512, 8, None) == _lib.ERR_ARG
+    # the tensor-core GEMMs of the fused UNet (K9, K10) and conv_in (K11): shapes and alignment are checked before any device work
+    assert lib.bndm_linear_tc_f32(fake, fake, None, fake, 256, 512, 100, None) == _lib.ERR_UNSUPPORTED and "multiple of 32" in err()
+    assert lib.bndm_linear_tc_f32(fake, None, None, fake, 256, 512, 128, None) == _lib.ERR_ARG
+    assert lib.bndm_linear_tc_f32(C.c_void_p(4100), fake, None, fake, 256, 512, 128, None) == _lib.ERR_ARG and "aligned" in err()
+    assert lib.bndm_shortcut_residual_tf32(fake, None, 128, 64, fake, fake, None, fake, 4096, 128, None) == _lib.ERR_ARG     # C2 > 0 without x2
+    assert lib.bndm_shortcut_residual_tf32(fake, fake, 120, 64, fake, fake, None, fake, 4096, 128, None) == _lib.ERR_UNSUPPORTED
+    assert lib.bndm_shortcut_residual_tf32(fake, fake, 128, 64, fake, None, None, fake, 4096, 128, None) == _lib.ERR_ARG
+    assert lib.bndm_conv_in3x3_nhwc_f32(fake, fake, None, 1, 3, 8, 8, 128, None) == _lib.ERR_ARG
     assert lib.bndm_to_uint8_nhwc(fake, None, 1, 3, 64, 64, None) == _lib.ERR_ARG
     assert lib.bndm_white128_reinterpret_f32(fake, fake, 1, 3, None) == _lib.ERR_ARG and "in-place" in err()
     # the mapping the Python mirror applies
